@@ -1,0 +1,196 @@
+// Extension-field elements (Fq, Fq2 = Fq[u]/(u^2-13), Fq3 = Fq[u]/(u^3-11)) living in a
+// shared-memory "slab", operated on by a TEAM of DEG warps: warp c of the team owns coefficient c
+// of every element, for 32 independent curve operations (one per lane).
+//
+// Replaces multiexp/arith.cu:370-462 (Fp2, Karatsuba) and :465-613 (Fp3, Karatsuba), which ran one
+// element per 16-lane tile.  Here a tower product is DEG dot products of length DEG -- coefficient
+// c is sum_{i+j = c mod DEG} a_i * b_j * (NR if i+j >= DEG) -- each with ONE lazy Montgomery
+// reduction (fq_dot), the non-residue folded into the a-operand as a small unreduced multiple.
+// Cost per tower product: DEG * (DEG+1) * 576 MACs, identical to the reference's Karatsuba with
+// per-product reduction (3*1152, 6*1152) but perfectly balanced over the DEG warps and with no
+// cross-coefficient additions.
+//
+// Slab layout: element e, coefficient c, quad q (limbs 4q..4q+3) of lane l is the uint4 at
+//     slab[((e*DEG + c)*6 + q)*32 + l]
+// so every warp-wide LDS.128/STS.128 touches 512 contiguous bytes (bank-conflict free).
+//
+// Synchronisation contract (DEG > 1): only mul/sqr/mul_by_a/is_zero read sibling coefficients.
+// Each of them does  team_sync(); read+compute; team_sync(); store.  add/sub/neg/copy touch the
+// caller's own coefficient only and need no barrier.  With this discipline every operation may be
+// used in place.
+#pragma once
+#include "fq.cuh"
+
+namespace mnt753 {
+
+constexpr int QUADS = 6;    // uint4 per Fq element
+constexpr int LANES = 32;
+
+#ifdef MNT753_HOST_EMU
+#define MSM_FOR_COMP(c) for (int c = 0; c < DEG; ++c)
+#define MSM_NCOMP DEG
+#define MSM_CI(c) (c)
+#else
+#define MSM_FOR_COMP(c) const int c = comp;
+#define MSM_NCOMP 1
+#define MSM_CI(c) 0
+#endif
+
+// Field configuration: M = base modulus, DEG = tower degree, NR = non-residue,
+// AKIND selects the curve-coefficient multiplication (mul_by_a):
+//   0: G1, a = A0 (small integer)                          coeff_a * x
+//   1: MNT4753 G2 twist, a = (A0, 0)                       (A0*c0, A0*c1)        mnt4753_g2.cpp:31-34
+//   2: MNT6753 G2 twist, a = (0, 0, A0/NR.. )              (A1*c1, A1*c2, A0*c0) mnt6753_g2.cpp:38-41
+template <class M_, int DEG_, unsigned NR_, int AKIND_, unsigned A0_, unsigned A1_>
+struct FieldCfg {
+    typedef M_ M;
+    static constexpr int DEG = DEG_;
+    static constexpr unsigned NR = NR_;
+    static constexpr int AKIND = AKIND_;
+    static constexpr unsigned A0 = A0_, A1 = A1_;
+};
+
+template <class F>
+struct Team {
+    typedef typename F::M M;
+    static constexpr int DEG = F::DEG;
+
+    uint4 *slab;      // team slab base + lane
+    uint32_t *flags;  // DEG words of team-shared scratch (device, DEG > 1)
+    int comp;         // coefficient owned by this warp (device)
+    int bar_id;       // named barrier of this team (device, DEG > 1)
+
+    MSM_DEVICE uint4 *elem(int e, int c) const { return slab + ((e * DEG + c) * QUADS) * LANES; }
+
+    MSM_DEVICE void sync() const {
+#ifndef MNT753_HOST_EMU
+        if (DEG > 1) asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(DEG * 32) : "memory");
+        else __syncwarp();
+#endif
+    }
+
+    MSM_DEVICE void ld(fq_t &r, int e, int c) const {
+        const uint4 *p = elem(e, c);
+#pragma unroll
+        for (int q = 0; q < QUADS; ++q) {
+            uint4 v = p[q * LANES];
+            r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+        }
+    }
+    MSM_DEVICE void st(int e, int c, const fq_t &r, bool pred = true) const {
+        uint4 *p = elem(e, c);
+        if (pred) {
+#pragma unroll
+            for (int q = 0; q < QUADS; ++q) {
+                uint4 v;
+                v.x = r[4 * q]; v.y = r[4 * q + 1]; v.z = r[4 * q + 2]; v.w = r[4 * q + 3];
+                p[q * LANES] = v;
+            }
+        }
+    }
+
+    // d = a * b.  Deliberately NOT inlined on the device: one copy of the ~1.3k..2.7k-instruction
+    // unrolled dot product per field keeps the hot loop inside the instruction cache.
+#ifndef MNT753_HOST_EMU
+    __device__ __noinline__
+#endif
+    void mul(int d, int a, int b, bool pred = true) const {
+        fq_t res[MSM_NCOMP];
+        sync();
+        MSM_FOR_COMP(c) {
+            uint32_t aa[DEG][NLIMB];
+            BQuads<DEG> src;
+            src.stride = LANES;
+#pragma unroll
+            for (int i = 0; i < DEG; ++i) {
+                ld(aa[i], a, i);
+                if (i > c) fq_scale_unreduced(aa[i], aa[i], F::NR);
+                int j = c - i;
+                if (j < 0) j += DEG;
+                src.p[i] = elem(b, j);
+            }
+            fq_dot<M, DEG>(res[MSM_CI(c)], aa, src);
+        }
+        sync();
+        MSM_FOR_COMP(c) st(d, c, res[MSM_CI(c)], pred);
+    }
+    MSM_DEVICE void sqr(int d, int a, bool pred = true) const { mul(d, a, a, pred); }
+
+    MSM_DEVICE void add(int d, int a, int b, bool pred = true) const {
+        MSM_FOR_COMP(c) { fq_t x, y; ld(x, a, c); ld(y, b, c); fq_add<M>(x, x, y); st(d, c, x, pred); }
+    }
+    MSM_DEVICE void sub(int d, int a, int b, bool pred = true) const {
+        MSM_FOR_COMP(c) { fq_t x, y; ld(x, a, c); ld(y, b, c); fq_sub<M>(x, x, y); st(d, c, x, pred); }
+    }
+    MSM_DEVICE void dbl(int d, int a, bool pred = true) const {
+        MSM_FOR_COMP(c) { fq_t x; ld(x, a, c); fq_add<M>(x, x, x); st(d, c, x, pred); }
+    }
+    // d = neg ? -a : a   (per lane)
+    MSM_DEVICE void neg_if(int d, int a, bool neg, bool pred = true) const {
+        MSM_FOR_COMP(c) {
+            fq_t x, y; ld(x, a, c); fq_neg<M>(y, x);
+#pragma unroll
+            for (int i = 0; i < NLIMB; ++i) x[i] = neg ? y[i] : x[i];
+            st(d, c, x, pred);
+        }
+    }
+    MSM_DEVICE void copy(int d, int a, bool pred = true) const {
+        MSM_FOR_COMP(c) { fq_t x; ld(x, a, c); st(d, c, x, pred); }
+    }
+    MSM_DEVICE void set_zero(int d, bool pred = true) const {
+        MSM_FOR_COMP(c) { fq_t x;
+#pragma unroll
+            for (int i = 0; i < NLIMB; ++i) x[i] = 0;
+            st(d, c, x, pred); }
+    }
+    MSM_DEVICE void set_one(int d, bool pred = true) const {
+        MSM_FOR_COMP(c) { fq_t x;
+#pragma unroll
+            for (int i = 0; i < NLIMB; ++i) x[i] = (c == 0) ? M::R1(i) : 0u;
+            st(d, c, x, pred); }
+    }
+
+    // d = coeff_a * x  (see FieldCfg::AKIND)
+    MSM_DEVICE void mul_by_a(int d, int x, bool pred = true) const {
+        fq_t res[MSM_NCOMP];
+        sync();
+        MSM_FOR_COMP(c) {
+            fq_t v;
+            if (F::AKIND == 2) {
+                ld(v, x, c == 2 ? 0 : c + 1);
+                if (c == 2) fq_mul_small<M, F::A0>(res[MSM_CI(c)], v);
+                else fq_mul_small<M, F::A1>(res[MSM_CI(c)], v);
+            } else {
+                ld(v, x, c);
+                fq_mul_small<M, F::A0>(res[MSM_CI(c)], v);
+            }
+        }
+        sync();
+        MSM_FOR_COMP(c) st(d, c, res[MSM_CI(c)], pred);
+    }
+
+    // per-lane test, identical in every warp of the team
+    MSM_DEVICE bool is_zero(int e) const {
+#ifdef MNT753_HOST_EMU
+        bool z = true;
+        for (int c = 0; c < DEG; ++c) { fq_t x; ld(x, e, c); z = z && fq_is_zero(x); }
+        return z;
+#else
+        fq_t x;
+        ld(x, e, comp);
+        bool z = fq_is_zero(x);
+        if (DEG == 1) return z;
+        const unsigned lane = threadIdx.x & 31;
+        unsigned nzmask = __ballot_sync(0xffffffffu, !z);
+        sync();
+        if (lane == 0) flags[comp] = nzmask;
+        sync();
+        unsigned all = 0;
+#pragma unroll
+        for (int c = 0; c < DEG; ++c) all |= flags[c];
+        return !((all >> lane) & 1u);
+#endif
+    }
+};
+
+}  // namespace mnt753

@@ -1,0 +1,253 @@
+// 753-bit Montgomery arithmetic on 24 x 32-bit limbs held in registers (R = 2^768).
+//
+// Replaces multiexp/arith.cu:219-363 (Fp<modulus_info>: add/sub/neg/mul CIOS on one 64-bit limb per
+// lane of a 16-lane tile) and multiexp/fixnum.cu / primitives.cu of the reference.  Here one
+// thread owns a whole element; the product loop is a CIOS whose 32x32->64 products are accumulated
+// into two interleaved 64-bit-aligned accumulators ("even" at limb 0, "odd" at limb 1) so that
+// every product is ONE IMAD.WIDE.U32.X on an add-with-carry chain, the reduction multiplies by
+// compile-time modulus limbs (immediates), and the per-row >>32 is register renaming.
+//
+// fq_dot computes  (sum_k a_k * b_k) / R  mod p  for K <= 3 operand pairs with a single
+// interleaved reduction ("lazy reduction"): that is what the Fq2/Fq3 towers in fe.cuh are built
+// from (one dot product per output coefficient).
+#pragma once
+#include "mnt753_constants.h"
+#include "prim.cuh"
+
+namespace mnt753 {
+
+constexpr int NLIMB = 24;
+
+// modulus A: Fq(MNT4753) = Fr(MNT6753); modulus B: Fr(MNT4753) = Fq(MNT6753)
+struct ModA {
+    MSM_HD static constexpr uint32_t P(int j) { constexpr uint32_t t[NLIMB] = MNT753_MOD_A_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t R1(int j) { constexpr uint32_t t[NLIMB] = MNT753_R1_A_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t R2(int j) { constexpr uint32_t t[NLIMB] = MNT753_R2_A_U32; return t[j]; }
+    static constexpr uint32_t INV = MNT753_INV_A_U32;
+};
+struct ModB {
+    MSM_HD static constexpr uint32_t P(int j) { constexpr uint32_t t[NLIMB] = MNT753_MOD_B_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t R1(int j) { constexpr uint32_t t[NLIMB] = MNT753_R1_B_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t R2(int j) { constexpr uint32_t t[NLIMB] = MNT753_R2_B_U32; return t[j]; }
+    static constexpr uint32_t INV = MNT753_INV_B_U32;
+};
+
+typedef uint32_t fq_t[NLIMB];
+
+MSM_DEVICE bool fq_is_zero(const fq_t &a) {
+    uint32_t o = 0;
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) o |= a[i];
+    return o == 0;
+}
+
+// r = a - p if a >= p else a        (a < 2p)
+template <class M>
+MSM_DEVICE void fq_cond_sub(fq_t &r, const fq_t &a) {
+    fq_t t;
+    t[0] = prim::sub_cc(a[0], M::P(0));
+#pragma unroll
+    for (int i = 1; i < NLIMB; ++i) t[i] = prim::subc_cc(a[i], M::P(i));
+    uint32_t borrow = prim::subc(0, 0);  // 0xffffffff when a < p
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) r[i] = borrow ? a[i] : t[i];
+}
+
+// modular add: a, b canonical -> canonical (reference: arith.cu:258-267)
+template <class M>
+MSM_DEVICE void fq_add(fq_t &r, const fq_t &a, const fq_t &b) {
+    fq_t s;
+    s[0] = prim::add_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < NLIMB; ++i) s[i] = prim::addc_cc(a[i], b[i]);
+    // 2p < 2^754 so no carry out of limb 23
+    fq_cond_sub<M>(r, s);
+}
+
+// modular sub (reference: arith.cu:276-285)
+template <class M>
+MSM_DEVICE void fq_sub(fq_t &r, const fq_t &a, const fq_t &b) {
+    fq_t d;
+    d[0] = prim::sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < NLIMB; ++i) d[i] = prim::subc_cc(a[i], b[i]);
+    uint32_t borrow = prim::subc(0, 0);
+    // add back p masked by the borrow
+    r[0] = prim::add_cc(d[0], M::P(0) & borrow);
+#pragma unroll
+    for (int i = 1; i < NLIMB; ++i) r[i] = prim::addc_cc(d[i], M::P(i) & borrow);
+}
+
+// modular negation with 0 -> 0 (libff Fp_model::operator-; the reference kernel maps 0 -> p,
+// arith.cu:269-274, which is non-canonical and deliberately not inherited)
+template <class M>
+MSM_DEVICE void fq_neg(fq_t &r, const fq_t &a) {
+    uint32_t nz = fq_is_zero(a) ? 0u : 0xffffffffu;
+    fq_t t;
+    t[0] = prim::sub_cc(M::P(0), a[0]);
+#pragma unroll
+    for (int i = 1; i < NLIMB; ++i) t[i] = prim::subc_cc(M::P(i), a[i]);
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) r[i] = t[i] & nz;
+}
+
+// r = k * a mod p for a small compile-time k (curve coefficients 2, 11, 26, 121): left-to-right
+// double-and-add with modular adds (replaces the add-chain multipliers of arith.cu:81-216)
+template <class M, unsigned K>
+MSM_DEVICE void fq_mul_small(fq_t &r, const fq_t &a) {
+    static_assert(K >= 1, "k >= 1");
+    int top = 31;
+    while (!((K >> top) & 1)) --top;
+    fq_t acc;
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) acc[i] = a[i];
+#pragma unroll
+    for (int bit = top - 1; bit >= 0; --bit) {
+        fq_add<M>(acc, acc, acc);
+        if ((K >> bit) & 1) fq_add<M>(acc, acc, a);
+    }
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) r[i] = acc[i];
+}
+
+// r = c * a as a plain integer (NOT reduced); c <= 13 and a < p < 2^753 so the result is < 2^757
+// and still fits 24 limbs.  Used to fold the tower non-residue into one operand of a dot product.
+MSM_DEVICE void fq_scale_unreduced(fq_t &r, const fq_t &a, uint32_t c) {
+    uint32_t hi[NLIMB];
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) hi[i] = prim::mul_hi(a[i], c);
+    r[0] = prim::mul_lo(a[0], c);
+    r[1] = prim::mad_lo_cc(a[1], c, hi[0]);
+#pragma unroll
+    for (int i = 2; i < NLIMB; ++i) r[i] = prim::madc_lo_cc(a[i], c, hi[i - 1]);
+}
+
+// ---- multiplicand limb sources for fq_dot --------------------------------------------------
+// K operands whose limbs sit in "quad-interleaved" memory: quad q (limbs 4q..4q+3) of operand k is
+// the uint4 at p[k][q * stride].  Shared-memory slabs use stride 32 (one uint4 per lane), see fe.cuh.
+template <int K>
+struct BQuads {
+    const uint4 *p[K];
+    int stride;
+    uint4 cur[K];
+    MSM_DEVICE uint32_t get(int k, int i) {
+        if ((i & 3) == 0) cur[k] = p[k][(i >> 2) * stride];
+        return (i & 3) == 0 ? cur[k].x : (i & 3) == 1 ? cur[k].y : (i & 3) == 2 ? cur[k].z : cur[k].w;
+    }
+};
+// K operands already in registers
+template <int K>
+struct BRegs {
+    const uint32_t (*b)[NLIMB];
+    MSM_DEVICE uint32_t get(int k, int i) const { return b[k][i]; }
+};
+
+// r = (sum_{k<K} a[k] * b[k]) * R^-1 mod p, canonical.
+// Preconditions: sum_k a[k]*b[k] < p * R (true for canonical b and a[k] <= 13p, K <= 3).
+// Accumulator invariant: T = E + (O << 32), E has 25 words (aligned at limb 0), O has 24 words
+// (aligned at limb 1); T < 2^800 throughout, so neither chain ever carries out of its top word.
+template <class M, int K, class BSrc>
+MSM_DEVICE void fq_dot(fq_t &r, const uint32_t (&a)[K][NLIMB], BSrc &bsrc) {
+    uint32_t E[NLIMB + 1], O[NLIMB];
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) {
+        uint32_t nE[NLIMB + 1], nO[NLIMB];
+        const uint32_t b0 = bsrc.get(0, i);
+        if (i == 0) {
+#pragma unroll
+            for (int j = 0; j < NLIMB; j += 2) {
+                nE[j] = prim::mul_lo(a[0][j], b0);
+                nE[j + 1] = prim::mul_hi(a[0][j], b0);
+                nO[j] = prim::mul_lo(a[0][j + 1], b0);
+                nO[j + 1] = prim::mul_hi(a[0][j + 1], b0);
+            }
+            nE[NLIMB] = 0;
+        } else {
+            // T >>= 32 folded into this row: new E = old O with old E[1] added at word 0 (its
+            // carry has the weight of new O[0], where the next chain starts), new O[k] = old E[k+2].
+            nE[0] = prim::add_cc(O[0], E[1]);
+#pragma unroll
+            for (int j = 1; j < NLIMB; j += 2) {
+                nO[j - 1] = prim::madc_lo_cc(a[0][j], b0, E[j + 1]);
+                nO[j] = prim::madc_hi_cc(a[0][j], b0, (j + 2 <= NLIMB) ? E[(j + 2 <= NLIMB) ? j + 2 : 0] : 0u);
+            }
+            nE[0] = prim::mad_lo_cc(a[0][0], b0, nE[0]);
+            nE[1] = prim::madc_hi_cc(a[0][0], b0, O[1]);
+#pragma unroll
+            for (int j = 2; j < NLIMB; j += 2) {
+                nE[j] = prim::madc_lo_cc(a[0][j], b0, O[j]);
+                nE[j + 1] = prim::madc_hi_cc(a[0][j], b0, O[j + 1]);
+            }
+            nE[NLIMB] = prim::addc(0, 0);
+        }
+#pragma unroll
+        for (int j = 0; j <= NLIMB; ++j) E[j] = nE[j];
+#pragma unroll
+        for (int j = 0; j < NLIMB; ++j) O[j] = nO[j];
+
+#pragma unroll
+        for (int k = 1; k < K; ++k) {
+            const uint32_t bk = bsrc.get(k, i);
+            E[0] = prim::mad_lo_cc(a[k][0], bk, E[0]);
+            E[1] = prim::madc_hi_cc(a[k][0], bk, E[1]);
+#pragma unroll
+            for (int j = 2; j < NLIMB; j += 2) {
+                E[j] = prim::madc_lo_cc(a[k][j], bk, E[j]);
+                E[j + 1] = prim::madc_hi_cc(a[k][j], bk, E[j + 1]);
+            }
+            E[NLIMB] = prim::addc(E[NLIMB], 0);
+            O[0] = prim::mad_lo_cc(a[k][1], bk, O[0]);
+            O[1] = prim::madc_hi_cc(a[k][1], bk, O[1]);
+#pragma unroll
+            for (int j = 3; j < NLIMB; j += 2) {
+                O[j - 1] = prim::madc_lo_cc(a[k][j], bk, O[j - 1]);
+                O[j] = prim::madc_hi_cc(a[k][j], bk, O[j]);
+            }
+        }
+
+        // Montgomery step: make the low limb vanish
+        const uint32_t m = prim::mul_lo(E[0], M::INV);
+        E[0] = prim::mad_lo_cc(m, M::P(0), E[0]);
+        E[1] = prim::madc_hi_cc(m, M::P(0), E[1]);
+#pragma unroll
+        for (int j = 2; j < NLIMB; j += 2) {
+            E[j] = prim::madc_lo_cc(m, M::P(j), E[j]);
+            E[j + 1] = prim::madc_hi_cc(m, M::P(j), E[j + 1]);
+        }
+        E[NLIMB] = prim::addc(E[NLIMB], 0);
+        O[0] = prim::mad_lo_cc(m, M::P(1), O[0]);
+        O[1] = prim::madc_hi_cc(m, M::P(1), O[1]);
+#pragma unroll
+        for (int j = 3; j < NLIMB; j += 2) {
+            O[j - 1] = prim::madc_lo_cc(m, M::P(j), O[j - 1]);
+            O[j] = prim::madc_hi_cc(m, M::P(j), O[j]);
+        }
+    }
+    // final >>32 and merge: t[k] = O[k] + E[k+1]
+    fq_t t;
+    t[0] = prim::add_cc(O[0], E[1]);
+#pragma unroll
+    for (int k = 1; k < NLIMB; ++k) t[k] = prim::addc_cc(O[k], E[k + 1]);
+    fq_cond_sub<M>(r, t);
+}
+
+// plain Montgomery product of two register operands
+template <class M>
+MSM_DEVICE void fq_mul(fq_t &r, const fq_t &a, const fq_t &b) {
+    uint32_t aa[1][NLIMB];
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) aa[0][i] = a[i];
+    BRegs<1> src{reinterpret_cast<const uint32_t(*)[NLIMB]>(&b)};
+    fq_dot<M, 1>(r, aa, src);
+}
+
+// Montgomery -> plain integer (multiply by the integer 1), reference: Fr::from_monty, arith.cu:356-362
+template <class M>
+MSM_DEVICE void fq_from_mont(fq_t &r, const fq_t &a) {
+    fq_t one;
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) one[i] = (i == 0) ? 1u : 0u;
+    fq_mul<M>(r, a, one);
+}
+
+}  // namespace mnt753

@@ -1,0 +1,123 @@
+// CPU emulation harness for the limb-level device code (fq.cuh / fe.cuh / ec.cuh).
+// Compiled by tests/conftest.py with g++ -DMNT753_HOST_EMU: the PTX carry-chain primitives are
+// replaced by C++ equivalents (prim.cuh) and a Team runs its DEG coefficients sequentially, so the
+// exact same templates that the kernels instantiate are checked against the oracle on machines
+// without a GPU.  Test-only; never shipped.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../gpu_groth16_prover_3x_b200/csrc/curves.cuh"
+
+using namespace mnt753;
+
+namespace {
+
+template <class G>
+struct Emu {
+    typedef typename G::F F;
+    static constexpr int DEG = F::DEG;
+    static constexpr int NE = 12;
+    std::vector<uint4> slab;
+    Team<F> T;
+    Emu() : slab((size_t)NE * DEG * QUADS * LANES) {
+        memset(slab.data(), 0xA5, slab.size() * sizeof(uint4));
+        T.slab = slab.data() + 7;  // arbitrary lane
+        T.flags = nullptr;
+        T.comp = 0;
+        T.bar_id = 0;
+    }
+    void put(int e, const uint64_t *w) {  // DEG*12 u64 wire element
+        for (int c = 0; c < DEG; ++c) {
+            fq_t x;
+            memcpy(x, w + 12 * c, 96);
+            T.st(e, c, x);
+        }
+    }
+    void get(int e, uint64_t *w) {
+        for (int c = 0; c < DEG; ++c) {
+            fq_t x;
+            T.ld(x, e, c);
+            memcpy(w + 12 * c, x, 96);
+        }
+    }
+};
+
+const PtSlots SL = {0, 1, 2, 3, 4, 5, 6, 7, 8};
+
+template <class G>
+int field_op(int op, size_t n, const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    Emu<G> E;
+    const size_t st = 12 * Emu<G>::DEG;
+    for (size_t i = 0; i < n; ++i) {
+        E.put(0, a + i * st);
+        if (b) E.put(1, b + i * st);
+        switch (op) {
+            case 0: E.T.mul(2, 0, 1); break;
+            case 1: E.T.add(2, 0, 1); break;
+            case 2: E.T.sub(2, 0, 1); break;
+            case 3: E.T.sqr(2, 0); break;
+            case 5: E.T.neg_if(2, 0, true); break;
+            case 6: E.T.mul_by_a(2, 0); break;
+            case 7: E.T.mul(0, 0, 1); E.T.copy(2, 0); break;  // in place
+            case 8: E.T.dbl(2, 0); break;
+            default: return -1;
+        }
+        E.get(2, out + i * st);
+    }
+    return 0;
+}
+
+// op 0: madd (acc jacobian, p affine x||y, flags: bit0 neg, bit1 acc_inf) -> acc jacobian, returns acc_inf
+// op 1: add  (acc jacobian, q jacobian)
+// op 2: dbl
+template <class G>
+int point_op(int op, const uint64_t *acc, const uint64_t *q, int flags, uint64_t *out) {
+    Emu<G> E;
+    const size_t st = 12 * Emu<G>::DEG;
+    E.put(0, acc); E.put(1, acc + st); E.put(2, acc + 2 * st);
+    bool acc_inf = flags & 2;
+    int ret = 0;
+    if (op == 0) {
+        E.put(3, q); E.put(4, q + st);
+        Ec<typename G::F>::madd(E.T, SL, flags & 1, true, acc_inf);
+        ret = acc_inf;
+        if (acc_inf) E.T.set_zero(2);
+    } else if (op == 1) {
+        E.put(3, q); E.put(4, q + st); E.put(5, q + 2 * st);
+        Ec<typename G::F>::add(E.T, SL, true);
+    } else if (op == 2) {
+        Ec<typename G::F>::dbl(E.T, SL, true);
+    } else return -1;
+    E.get(0, out); E.get(1, out + st); E.get(2, out + 2 * st);
+    return ret;
+}
+
+}  // namespace
+
+extern "C" {
+int emu_field_op(int curve, int group, int op, size_t n, const uint64_t *a, const uint64_t *b, uint64_t *out) {
+    if (curve == 0 && group == 1) return field_op<Mnt4G1>(op, n, a, b, out);
+    if (curve == 0 && group == 2) return field_op<Mnt4G2>(op, n, a, b, out);
+    if (curve == 1 && group == 1) return field_op<Mnt6G1>(op, n, a, b, out);
+    if (curve == 1 && group == 2) return field_op<Mnt6G2>(op, n, a, b, out);
+    return -1;
+}
+int emu_point_op(int curve, int group, int op, const uint64_t *acc, const uint64_t *q, int flags, uint64_t *out) {
+    if (curve == 0 && group == 1) return point_op<Mnt4G1>(op, acc, q, flags, out);
+    if (curve == 0 && group == 2) return point_op<Mnt4G2>(op, acc, q, flags, out);
+    if (curve == 1 && group == 1) return point_op<Mnt6G1>(op, acc, q, flags, out);
+    if (curve == 1 && group == 2) return point_op<Mnt6G2>(op, acc, q, flags, out);
+    return -1;
+}
+// scalar-field helper used by the digit kernel: Montgomery -> integer
+int emu_fr_from_mont(int curve, size_t n, const uint64_t *in, uint64_t *out) {
+    for (size_t i = 0; i < n; ++i) {
+        fq_t x, r;
+        memcpy(x, in + 12 * i, 96);
+        if (curve == 0) fq_from_mont<ModB>(r, x); else fq_from_mont<ModA>(r, x);
+        memcpy(out + 12 * i, r, 96);
+    }
+    return 0;
+}
+}
