@@ -31,7 +31,7 @@ constexpr int LANES = 32;
 #define MSM_NCOMP DEG
 #define MSM_CI(c) (c)
 #else
-#define MSM_FOR_COMP(c) const int c = comp;
+#define MSM_FOR_COMP(c) for (int c = comp, once_ = 1; once_; once_ = 0)
 #define MSM_NCOMP 1
 #define MSM_CI(c) 0
 #endif

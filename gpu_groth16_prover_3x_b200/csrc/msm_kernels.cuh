@@ -1,0 +1,505 @@
+// Pippenger MSM pipeline kernels (replaces multiexp/reduce.cu:11-152 of the reference: the
+// precomputed-multiples Straus kernel + pairwise tree is gone, and so is the 31x table).
+//
+//   k_flag_inf        once per base set: mark bases encoded as infinity (y == 0)
+//   k_from_mont       scalars: Montgomery -> integer (reference: reduce.cu:35-36)
+//   k_count           signed-digit recode, histogram of (window, bucket) keys
+//   k_scan_*          exclusive prefix sum of the histogram
+//   k_scatter         single-pass radix (counting) sort: point indices grouped by (window, bucket)
+//   k_accumulate      bucket accumulation: each lane walks a fixed-length chunk of the sorted list,
+//                     streaming affine bases from HBM (128-bit cp.async into the team slab), one
+//                     mixed addition per entry; runs that cover a whole bucket are written straight
+//                     to the bucket array, runs cut by a chunk border go to an edge list
+//   k_fixup           folds edge partial sums of buckets that span several chunks
+//   k_bucket_reduce   per (window, segment): running-sum reduction  sum_b b*B_b  of a bucket segment
+//   k_sum             plain segmented sums (segment sums -> window sums)
+//   k_horner          window combine: result = sum_w 2^(c*w) * S_w
+//
+// Work decomposition: a TEAM = DEG warps handles 32 lanes (see fe.cuh); blocks hold TPB teams.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "curves.cuh"
+
+namespace mnt753 {
+
+constexpr uint32_t EDGE_NONE = 0xffffffffu;
+
+struct MsmArgs {
+    // problem
+    uint32_t n;        // number of points
+    int c;             // window width in bits
+    int W;             // number of windows
+    uint32_t NB;       // buckets per window = 2^(c-1)
+    uint32_t K;        // W * NB
+    uint32_t L;        // sorted-list entries per lane chunk
+    uint32_t max_chunks;
+    uint32_t m;        // bucket-reduce segment length (power of two)
+    uint32_t nseg;     // NB / m
+    // buffers
+    const uint32_t *bases;      // affine AoS, 2*DEG*24 words per point
+    const uint8_t *base_inf;    // 1 if base is infinity
+    uint32_t *scalars;          // n * 24 words; Montgomery in, plain integer after k_from_mont
+    uint32_t *count;            // K
+    uint32_t *offs;             // K + 1
+    uint32_t *cursor;           // K
+    uint32_t *entries;          // n * W : point index | sign << 31
+    uint32_t *buckets;          // K Jacobian points (3*DEG*24 words each)
+    uint32_t *edges;            // max_chunks * 2 Jacobian points
+    uint32_t *edge_bucket;      // max_chunks * 2
+    uint32_t *segsum;           // W * nseg Jacobian points
+    uint32_t *tmp_a, *tmp_b;    // scratch point arrays for k_sum levels
+    uint32_t *winsum;           // W Jacobian points
+    uint32_t *result;           // 1 Jacobian point
+    uint32_t *group_counter;    // dynamic work counter for k_accumulate
+};
+
+// ------------------------------------------------------------------------------------------
+// kernel-side team construction
+template <class G, int NSLOT, int TPB>
+struct TeamSetup {
+    typedef typename G::F F;
+    static constexpr int DEG = F::DEG;
+    static constexpr int THREADS = TPB * DEG * 32;
+    static constexpr size_t SMEM = (size_t)TPB * NSLOT * DEG * QUADS * LANES * sizeof(uint4);
+    __device__ static Team<F> make(uint4 *smem, uint32_t (*flags)[4], int &team) {
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        team = warp / DEG;
+        Team<F> T;
+        T.slab = smem + (size_t)team * (NSLOT * DEG * QUADS * LANES) + lane;
+        T.flags = flags[team];
+        T.comp = warp % DEG;
+        T.bar_id = 1 + team;
+        return T;
+    }
+};
+
+// global <-> slab movement of one coefficient (96 B contiguous in global memory)
+template <class F>
+__device__ __forceinline__ void g2s(const Team<F> &T, int slot, const uint32_t *g, bool pred) {
+    if (pred) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g) + T.comp * QUADS;
+        uint4 *dst = T.elem(slot, T.comp);
+#pragma unroll
+        for (int q = 0; q < QUADS; ++q) dst[q * LANES] = src[q];
+    }
+}
+template <class F>
+__device__ __forceinline__ void s2g(const Team<F> &T, uint32_t *g, int slot, bool pred) {
+    if (pred) {
+        uint4 *dst = reinterpret_cast<uint4 *>(g) + T.comp * QUADS;
+        const uint4 *src = T.elem(slot, T.comp);
+#pragma unroll
+        for (int q = 0; q < QUADS; ++q) dst[q] = src[q * LANES];
+    }
+}
+// asynchronous 128-bit global -> shared copies (LDGSTS)
+template <class F>
+__device__ __forceinline__ void g2s_async(const Team<F> &T, int slot, const uint32_t *g, bool pred) {
+    if (pred) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(g) + T.comp * QUADS;
+        uint4 *dst = T.elem(slot, T.comp);
+#pragma unroll
+        for (int q = 0; q < QUADS; ++q) {
+            unsigned saddr = (unsigned)__cvta_generic_to_shared(dst + q * LANES);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(src + q) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <class F>
+__device__ __forceinline__ void load_jac(const Team<F> &T, int X, int Y, int Z, const uint32_t *g, bool pred) {
+    constexpr int EW = F::DEG * NLIMB;
+    g2s(T, X, g, pred);
+    g2s(T, Y, g + EW, pred);
+    g2s(T, Z, g + 2 * EW, pred);
+}
+template <class F>
+__device__ __forceinline__ void store_jac(const Team<F> &T, uint32_t *g, int X, int Y, int Z, bool pred) {
+    constexpr int EW = F::DEG * NLIMB;
+    s2g(T, g, X, pred);
+    s2g(T, g + EW, Y, pred);
+    s2g(T, g + 2 * EW, Z, pred);
+}
+
+// ------------------------------------------------------------------------------------------
+template <int DEG>
+__global__ void k_flag_inf(const uint32_t *bases, uint32_t n, uint8_t *flag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint4 *y = reinterpret_cast<const uint4 *>(bases + (size_t)i * 2 * DEG * NLIMB + DEG * NLIMB);
+    uint32_t o = 0;
+    for (int q = 0; q < DEG * QUADS; ++q) { uint4 v = y[q]; o |= v.x | v.y | v.z | v.w; }
+    flag[i] = (o == 0);
+}
+
+template <class Fr>
+__global__ void __launch_bounds__(128) k_from_mont(uint32_t *scalars, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint4 *p = reinterpret_cast<uint4 *>(scalars + (size_t)i * NLIMB);
+    fq_t x, r;
+#pragma unroll
+    for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w; }
+    fq_from_mont<Fr>(r, x);
+#pragma unroll
+    for (int q = 0; q < QUADS; ++q) { uint4 v; v.x = r[4 * q]; v.y = r[4 * q + 1]; v.z = r[4 * q + 2]; v.w = r[4 * q + 3]; p[q] = v; }
+}
+
+// signed-digit recoding of a 753-bit integer into W windows of c bits: digits in
+// [-2^(c-1)+1, 2^(c-1)], a borrow of 2^c carried into the next window; W*c >= 754 so the top
+// window never overflows.  f(w, digit) is called for non-zero digits only.
+template <class Fn>
+__device__ __forceinline__ void for_each_digit(const uint32_t *k, int c, int W, Fn f) {
+    uint32_t carry = 0;
+    const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
+    for (int w = 0; w < W; ++w) {
+        const int o = w * c, word = o >> 5, sh = o & 31;
+        uint64_t v = k[word];
+        if (word + 1 < NLIMB) v |= (uint64_t)k[word + 1] << 32;
+        uint32_t raw = ((uint32_t)(v >> sh) & mask) + carry;
+        int d;
+        if (raw > half) { d = (int)raw - (int)(1u << c); carry = 1; } else { d = (int)raw; carry = 0; }
+        if (d != 0) f(w, d);
+    }
+}
+
+__global__ void k_count(MsmArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n || a.base_inf[i]) return;
+    uint32_t k[NLIMB];
+    const uint4 *p = reinterpret_cast<const uint4 *>(a.scalars + (size_t)i * NLIMB);
+    for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w; }
+    for_each_digit(k, a.c, a.W, [&](int w, int d) {
+        uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
+        atomicAdd(&a.count[(uint32_t)w * a.NB + b], 1u);
+    });
+}
+
+__global__ void k_scatter(MsmArgs a) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n || a.base_inf[i]) return;
+    uint32_t k[NLIMB];
+    const uint4 *p = reinterpret_cast<const uint4 *>(a.scalars + (size_t)i * NLIMB);
+    for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w; }
+    for_each_digit(k, a.c, a.W, [&](int w, int d) {
+        uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
+        uint32_t pos = atomicAdd(&a.cursor[(uint32_t)w * a.NB + b], 1u);
+        a.entries[pos] = i | (d < 0 ? 0x80000000u : 0u);
+    });
+}
+
+// ---- exclusive scan of count[0..K) -> offs[0..K], offs[K] = total -----------------------------
+constexpr int SCAN_T = 256, SCAN_E = 4, SCAN_B = SCAN_T * SCAN_E;
+__global__ void __launch_bounds__(SCAN_T) k_scan_local(const uint32_t *in, uint32_t *out, uint32_t *bsum, uint32_t K) {
+    __shared__ uint32_t sh[SCAN_T];
+    uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
+    uint32_t v[SCAN_E], s = 0;
+    for (int e = 0; e < SCAN_E; ++e) { v[e] = (base + e < K) ? in[base + e] : 0u; s += v[e]; }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    for (int d = 1; d < SCAN_T; d <<= 1) {
+        uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t excl = sh[threadIdx.x] - s;
+    for (int e = 0; e < SCAN_E; ++e) { if (base + e < K) out[base + e] = excl; excl += v[e]; }
+    if (threadIdx.x == SCAN_T - 1) bsum[blockIdx.x] = sh[SCAN_T - 1];
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_bsum(uint32_t *bsum, uint32_t nb, uint32_t *total) {
+    __shared__ uint32_t sh[SCAN_T];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < nb; base += SCAN_T) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t s = (i < nb) ? bsum[i] : 0u;
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int d = 1; d < SCAN_T; d <<= 1) {
+            uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nb) bsum[i] = carry + sh[threadIdx.x] - s;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[SCAN_T - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t *out, uint32_t *cursor, const uint32_t *bsum, uint32_t K) {
+    uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
+    uint32_t add = bsum[blockIdx.x];
+    for (int e = 0; e < SCAN_E; ++e)
+        if (base + e < K) { uint32_t v = out[base + e] + add; out[base + e] = v; cursor[base + e] = v; }
+}
+
+// first index i in [0, n] with offs[i] > x, minus one  (offs non-decreasing, offs[0] = 0 <= x < offs[n])
+__device__ __forceinline__ uint32_t bucket_of(const uint32_t *offs, uint32_t n, uint32_t x) {
+    uint32_t lo = 0, hi = n;  // invariant: offs[lo] <= x < offs[hi]
+    while (hi - lo > 1) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (offs[mid] <= x) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------------------
+// bucket accumulation
+template <class G>
+struct AccCfg {
+    static constexpr int DEG = G::F::DEG;
+    static constexpr int NSLOT = 8;
+    static constexpr int TPB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 1);
+    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 3);
+    typedef TeamSetup<G, NSLOT, TPB> TS;
+};
+
+template <class G>
+__global__ void __launch_bounds__(AccCfg<G>::TS::THREADS, AccCfg<G>::MINB) k_accumulate(MsmArgs a) {
+    typedef typename G::F F;
+    typedef AccCfg<G> C;
+    constexpr int DEG = F::DEG;
+    constexpr int AFFW = 2 * DEG * NLIMB, JACW = 3 * DEG * NLIMB, EW = DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    __shared__ uint32_t s_group[C::TPB];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const int lane = threadIdx.x & 31;
+    const PtSlots s = {0, 1, 2, 3, 4, 4, 5, 6, 7};
+
+    const uint32_t E = a.offs[a.K];
+    const uint32_t nchunks = (uint32_t)(((uint64_t)E + a.L - 1) / a.L);
+    const uint32_t ngroups = (nchunks + 31) / 32;
+
+    for (;;) {
+        T.sync();
+        if (T.comp == 0 && lane == 0) s_group[team] = atomicAdd(a.group_counter, 1u);
+        T.sync();
+        const uint32_t grp = s_group[team];
+        if (grp >= ngroups) break;
+        const uint32_t chunk = grp * 32 + lane;
+        const bool has_chunk = chunk < nchunks;
+        const uint32_t cstart = has_chunk ? chunk * a.L : 0u;
+        const uint32_t cend = has_chunk ? (uint32_t)min((uint64_t)cstart + a.L, (uint64_t)E) : 0u;
+        uint32_t pos = cstart;
+        uint32_t b = 0, bstart = 0, bend = 0;
+        if (has_chunk) {
+            b = bucket_of(a.offs, a.K, cstart);
+            bstart = a.offs[b];
+            bend = a.offs[b + 1];
+            if (T.comp == 0) { a.edge_bucket[2 * chunk] = EDGE_NONE; a.edge_bucket[2 * chunk + 1] = EDGE_NONE; }
+        }
+        bool acc_inf = true;
+        bool neg_next = false;
+        {
+            const bool act = has_chunk && pos < cend;
+            uint32_t e = act ? a.entries[pos] : 0u;
+            neg_next = e >> 31;
+            const uint32_t *src = a.bases + (size_t)(e & 0x7fffffffu) * AFFW;
+            g2s_async(T, s.X2, src, act);
+            g2s_async(T, s.Y2, src + EW, act);
+        }
+        auto flush = [&](bool pred) {
+            // run of bucket b inside this chunk is finished
+            const bool complete = bstart >= cstart && bend <= cend;
+            const uint32_t which = bstart < cstart ? 0u : 1u;
+            uint32_t *dst = complete ? a.buckets + (size_t)b * JACW : a.edges + ((size_t)chunk * 2 + which) * JACW;
+            if (pred && !complete && T.comp == 0) a.edge_bucket[2 * chunk + which] = b;
+            T.set_zero(s.Z1, pred && acc_inf);
+            store_jac(T, dst, s.X1, s.Y1, s.Z1, pred);
+        };
+        for (uint32_t step = 0; step < a.L; ++step) {
+            const bool active = has_chunk && pos < cend;
+            if (!team_any(active)) break;
+            const bool fl = active && pos == bend;
+            if (team_any(fl)) {
+                flush(fl);
+                if (fl) {
+                    acc_inf = true;
+                    do { ++b; } while (a.offs[b + 1] <= pos);
+                    bstart = a.offs[b];
+                    bend = a.offs[b + 1];
+                }
+            }
+            const bool neg = neg_next;
+            async_wait_all();
+            Ec<F>::madd_head(T, s, neg, active, acc_inf);
+            {
+                const bool act = active && pos + 1 < cend;
+                uint32_t e = act ? a.entries[pos + 1] : 0u;
+                neg_next = e >> 31;
+                const uint32_t *src = a.bases + (size_t)(e & 0x7fffffffu) * AFFW;
+                g2s_async(T, s.X2, src, act);
+                g2s_async(T, s.Y2, src + EW, act);
+            }
+            Ec<F>::madd_tail(T, s, neg, active, acc_inf);
+            if (active) ++pos;
+        }
+        async_wait_all();
+        flush(has_chunk && cend > cstart);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic tail kernels: 12 slots  TOT(0-2) RUN(3-5) Q(6-8) T(9-11)
+template <class G>
+struct TailCfg {
+    static constexpr int DEG = G::F::DEG;
+    static constexpr int NSLOT = 12;
+    static constexpr int TPB = DEG == 1 ? 2 : 1;
+    typedef TeamSetup<G, NSLOT, TPB> TS;
+};
+
+// fold edge partials: lane = chunk whose edge[1] starts a chain
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_fixup(MsmArgs a) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    constexpr int JACW = 3 * F::DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const int lane = threadIdx.x & 31;
+    const PtSlots s = {0, 1, 2, 6, 7, 8, 9, 10, 11};
+    const uint32_t E = a.offs[a.K];
+    const uint32_t nchunks = (uint32_t)(((uint64_t)E + a.L - 1) / a.L);
+    const uint32_t chunk = (blockIdx.x * C::TPB + team) * 32 + lane;
+    uint32_t b = EDGE_NONE;
+    if (chunk < nchunks) b = a.edge_bucket[2 * chunk + 1];
+    bool head = b != EDGE_NONE;
+    if (!team_any(head)) return;
+    load_jac(T, s.X1, s.Y1, s.Z1, a.edges + ((size_t)chunk * 2 + 1) * JACW, head);
+    T.set_zero(s.Z1, !head);
+    uint32_t j = chunk + 1;
+    bool going = head;
+    for (;;) {
+        const bool cont = going && j < nchunks && a.edge_bucket[2 * j] == b;
+        if (!team_any(cont)) break;
+        load_jac(T, s.X2, s.Y2, s.Z2, a.edges + (size_t)j * 2 * JACW, cont);
+        T.set_zero(s.Z2, !cont);
+        Ec<F>::add(T, s, cont);
+        if (cont) ++j; else going = false;
+    }
+    store_jac(T, a.buckets + (size_t)b * JACW, s.X1, s.Y1, s.Z1, head);
+}
+
+// running-sum reduction of one bucket segment per lane; out[w*nseg + seg] = sum_{j<m} (seg*m+j+1) * B[w][seg*m+j]
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_bucket_reduce(MsmArgs a) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    constexpr int JACW = 3 * F::DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const int lane = threadIdx.x & 31;
+    const PtSlots tot = {0, 1, 2, 6, 7, 8, 9, 10, 11};
+    const PtSlots run = {3, 4, 5, 6, 7, 8, 9, 10, 11};
+    const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + lane;
+    const bool valid = id < (uint32_t)a.W * a.nseg;
+    const uint32_t w = valid ? id / a.nseg : 0u, seg = valid ? id % a.nseg : 0u;
+    T.set_zero(tot.Z1);
+    T.set_zero(run.Z1);
+    bool run_inf = true;
+    for (int j = (int)a.m - 1; j >= 0; --j) {
+        const uint32_t key = w * a.NB + seg * a.m + (uint32_t)j;
+        const bool ne = valid && a.offs[key + 1] > a.offs[key];
+        if (team_any(ne)) {
+            load_jac(T, run.X2, run.Y2, run.Z2, a.buckets + (size_t)key * JACW, ne);
+            T.set_zero(run.Z2, !ne);
+            Ec<F>::add(T, run, ne);
+            run_inf = run_inf && !ne;
+        }
+        if (team_any(!run_inf)) {
+            T.copy(tot.X2, run.X1); T.copy(tot.Y2, run.Y1); T.copy(tot.Z2, run.Z1);
+            Ec<F>::add(T, tot, !run_inf);
+        }
+    }
+    // out = tot + (seg*m) * run : park tot in global, reuse its slots for the scalar multiple
+    uint32_t *out = a.segsum + (size_t)id * JACW;
+    store_jac(T, out, tot.X1, tot.Y1, tot.Z1, valid);
+    T.set_zero(tot.Z1);
+    const uint32_t k = seg * a.m;
+    int top = 31 - __clz(max(a.NB, 2u) - 1u);  // highest possible bit of k
+    for (int bit = top; bit >= 0; --bit) {
+        Ec<F>::dbl(T, tot, true);
+        const bool on = valid && ((k >> bit) & 1u) && !run_inf;
+        if (team_any(on)) {
+            T.copy(tot.X2, run.X1); T.copy(tot.Y2, run.Y1); T.copy(tot.Z2, run.Z1);
+            Ec<F>::add(T, tot, on);
+        }
+    }
+    T.sync();
+    load_jac(T, tot.X2, tot.Y2, tot.Z2, out, valid);
+    T.set_zero(tot.Z2, !valid);
+    Ec<F>::add(T, tot, valid);
+    store_jac(T, out, tot.X1, tot.Y1, tot.Z1, valid);
+}
+
+// out[w*nout + o] = sum_{j<m} in[w*nin + o*m + j]   (nout = ceil(nin/m))
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_sum(const uint32_t *in, uint32_t *out, uint32_t W, uint32_t nin, uint32_t m) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    constexpr int JACW = 3 * F::DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const int lane = threadIdx.x & 31;
+    const PtSlots s = {0, 1, 2, 6, 7, 8, 9, 10, 11};
+    const uint32_t nout = (nin + m - 1) / m;
+    const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + lane;
+    const bool valid = id < W * nout;
+    const uint32_t w = valid ? id / nout : 0u, o = valid ? id % nout : 0u;
+    T.set_zero(s.Z1);
+    for (uint32_t j = 0; j < m; ++j) {
+        const uint32_t idx = o * m + j;
+        const bool act = valid && idx < nin;
+        if (!team_any(act)) break;
+        load_jac(T, s.X2, s.Y2, s.Z2, in + ((size_t)w * nin + idx) * JACW, act);
+        T.set_zero(s.Z2, !act);
+        Ec<F>::add(T, s, act);
+    }
+    store_jac(T, out + (size_t)id * JACW, s.X1, s.Y1, s.Z1, valid);
+}
+
+// result = sum_w 2^(c*w) * winsum[w]   (one lane; the other 31 idle)
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_horner(MsmArgs a) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    constexpr int JACW = 3 * F::DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    if (team != 0) return;
+    const int lane = threadIdx.x & 31;
+    const PtSlots s = {0, 1, 2, 6, 7, 8, 9, 10, 11};
+    const bool me = lane == 0;
+    T.set_zero(s.Z1);
+    for (int w = a.W - 1; w >= 0; --w) {
+        if (w != a.W - 1)
+            for (int i = 0; i < a.c; ++i) Ec<F>::dbl(T, s, true);
+        load_jac(T, s.X2, s.Y2, s.Z2, a.winsum + (size_t)w * JACW, me);
+        T.set_zero(s.Z2, !me);
+        Ec<F>::add(T, s, me);
+    }
+    // infinity is reported as (1, 1, 0) like the reference's ec_jac::set_zero (curves.cu:104-114)
+    const bool inf = T.is_zero(s.Z1);
+    T.set_one(s.X1, inf);
+    T.set_one(s.Y1, inf);
+    store_jac(T, a.result, s.X1, s.Y1, s.Z1, me);
+}
+
+}  // namespace mnt753

@@ -1,0 +1,234 @@
+"""ctypes mirror of include/b200_msm.h.
+
+Vocabulary follows the reference: a *base set* is one query of the proving key (A, B1, L, H in G1,
+B2 in G2; cuda_prover_piecewise.cu:132-139), scalars are Montgomery-form Fr elements (12 x u64), the
+result of an MSM is one Jacobian point X||Y||Z that B::read_pt_ECp / read_pt_ECpe consume
+(prover_reference_functions.cpp:795-817).
+"""
+import ctypes
+import os
+
+import numpy as np
+
+MNT4753, MNT6753 = 0, 1
+G1, G2 = 1, 2
+_ERRORS = {1: "invalid argument", 2: "CUDA error / no usable sm_100 device", 3: "out of device memory"}
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u32p = ctypes.POINTER(ctypes.c_uint32)
+_lib = None
+
+
+class MsmError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("b200msm error %d (%s): %s" % (code, _ERRORS.get(code, "?"), msg))
+        self.code = code
+
+
+def degree(curve, group):
+    """Extension degree of the coordinate field: 1 (G1), 2 (MNT4753 G2), 3 (MNT6753 G2)."""
+    return 1 if group == G1 else (2 if curve == MNT4753 else 3)
+
+
+def library_path():
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200msm.so")
+
+
+def load_library():
+    """Load libb200msm.so.  There is no fallback: a missing library is an error."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = library_path()
+    if not os.path.exists(path):
+        raise ImportError("%s is missing: build it with `python -m gpu_groth16_prover_3x_b200.build` "
+                          "(or __graft_entry__.build()); the MSM engine has no CPU fallback" % path)
+    lib = ctypes.CDLL(path)
+    vp, ci, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    lib.b200msm_create.argtypes = [ci, ci, ctypes.POINTER(vp)]
+    lib.b200msm_destroy.argtypes = [vp]
+    lib.b200msm_destroy.restype = None
+    lib.b200msm_last_error.argtypes = [vp]
+    lib.b200msm_last_error.restype = ctypes.c_char_p
+    lib.b200msm_bases_upload.argtypes = [vp, ci, vp, sz, ctypes.POINTER(ci)]
+    lib.b200msm_bases_free.argtypes = [vp, ci]
+    lib.b200msm_msm.argtypes = [vp, ci, sz, vp, sz, vp]
+    lib.b200msm_msm_async.argtypes = [vp, ci, ci, sz, vp, sz, vp]
+    lib.b200msm_wait.argtypes = [vp, ci]
+    lib.b200msm_ec_reduce.argtypes = [vp, ci, vp, vp, sz, vp]
+    lib.b200msm_fold.argtypes = [vp, ci, vp, sz, vp]
+    lib.b200msm_set_window_bits.argtypes = [vp, ci]
+    lib.b200msm_last_timings.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), _u64p]
+    lib.b200msm_microbench.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double)]
+    lib.b200msm_selftest_field.argtypes = [vp, ci, ci, sz, vp, vp, vp]
+    lib.b200msm_selftest_point.argtypes = [vp, ci, ci, sz, vp, vp, vp, vp]
+    _lib = lib
+    return lib
+
+
+def shard_ranges(n, parts):
+    """Point-range sharding of an MSM of n points over `parts` GPUs: contiguous,
+    sizes differ by at most one, in order.  -> list of (offset, length)."""
+    base, extra = divmod(n, parts)
+    out, off = [], 0
+    for i in range(parts):
+        ln = base + (1 if i < extra else 0)
+        out.append((off, ln))
+        off += ln
+    return out
+
+
+def _ptr(x):
+    """Address of a numpy array (host) or torch tensor (host or device); None -> NULL."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        assert x.flags["C_CONTIGUOUS"]
+        return x.ctypes.data
+    if isinstance(x, int):
+        return x
+    assert x.is_contiguous()
+    return x.data_ptr()
+
+
+def _nbytes(x):
+    return x.nbytes if isinstance(x, np.ndarray) else x.numel() * x.element_size()
+
+
+class MsmContext:
+    """One engine context per (curve, GPU)."""
+
+    PHASES = ("total", "h2d_scalars", "recode_sort", "accumulate", "reduce_combine", "d2h_result")
+
+    def __init__(self, curve, device=0):
+        self.lib = load_library()
+        self.curve = curve
+        self.device = device
+        self._h = ctypes.c_void_p()
+        rc = self.lib.b200msm_create(curve, device, ctypes.byref(self._h))
+        if rc:
+            self._h = ctypes.c_void_p()
+            raise MsmError(rc, "b200msm_create(curve=%d, device=%d) failed" % (curve, device))
+        self._slot_group = {}
+        self._pending = {}
+
+    def close(self):
+        if self._h:
+            self.lib.b200msm_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise MsmError(rc, self.lib.b200msm_last_error(self._h).decode())
+
+    # ---- base sets ---------------------------------------------------------------------------
+    def upload_bases(self, group, affine, n=None):
+        """affine: n points x||y in the wire format (uint64 limbs; host array or device tensor)."""
+        per = 24 * degree(self.curve, group) * 8
+        if n is None:
+            n = _nbytes(affine) // per
+        assert _nbytes(affine) >= n * per
+        slot = ctypes.c_int(-1)
+        self._check(self.lib.b200msm_bases_upload(self._h, group, _ptr(affine), n, ctypes.byref(slot)))
+        self._slot_group[slot.value] = (group, n)
+        return slot.value
+
+    def free_bases(self, slot):
+        self._check(self.lib.b200msm_bases_free(self._h, slot))
+        self._slot_group.pop(slot, None)
+
+    # ---- MSM ---------------------------------------------------------------------------------
+    def _out(self, group):
+        return np.zeros(36 * degree(self.curve, group), np.uint64)
+
+    def msm(self, slot, scalars, n=None, offset=0):
+        """sum_i scalars[i] * bases[offset + i] -> Jacobian X||Y||Z (uint64[36*DEG])."""
+        group, nb = self._slot_group[slot]
+        if n is None:
+            n = _nbytes(scalars) // 96
+        out = self._out(group)
+        self._check(self.lib.b200msm_msm(self._h, slot, offset, _ptr(scalars), n, out.ctypes.data))
+        return out
+
+    def msm_async(self, lane, slot, scalars, n=None, offset=0):
+        group, nb = self._slot_group[slot]
+        if n is None:
+            n = _nbytes(scalars) // 96
+        out = self._out(group)
+        self._check(self.lib.b200msm_msm_async(self._h, lane, slot, offset, _ptr(scalars), n, out.ctypes.data))
+        self._pending[lane] = (out, scalars)  # keep both alive until wait()
+
+    def wait(self, lane):
+        self._check(self.lib.b200msm_wait(self._h, lane))
+        out, _ = self._pending.pop(lane)
+        return out
+
+    def ec_reduce(self, group, bases_affine, scalars, n=None):
+        """Literal counterpart of ec_reduce_straus (multiexp/reduce.cu:131-152): bases travel with the call."""
+        if n is None:
+            n = _nbytes(scalars) // 96
+        out = self._out(group)
+        self._check(self.lib.b200msm_ec_reduce(self._h, group, _ptr(bases_affine), _ptr(scalars), n, out.ctypes.data))
+        return out
+
+    # names of the reference's plugin API (prover_reference_functions.hpp:59-62)
+    def multiexp_G1(self, scalars, bases_affine, length=None):
+        return self.ec_reduce(G1, bases_affine, scalars, length)
+
+    def multiexp_G2(self, scalars, bases_affine, length=None):
+        return self.ec_reduce(G2, bases_affine, scalars, length)
+
+    def fold(self, group, partials_xyz):
+        """Sum of Jacobian partial results (one per GPU shard) -> one Jacobian point, on this GPU."""
+        per = 36 * degree(self.curve, group)
+        partials_xyz = np.ascontiguousarray(partials_xyz, dtype=np.uint64).reshape(-1)
+        n = partials_xyz.size // per
+        out = self._out(group)
+        self._check(self.lib.b200msm_fold(self._h, group, partials_xyz.ctypes.data, n, out.ctypes.data))
+        return out
+
+    # ---- tuning / introspection --------------------------------------------------------------
+    def set_window_bits(self, c):
+        self._check(self.lib.b200msm_set_window_bits(self._h, c))
+
+    def last_timings(self, lane=0):
+        ms = (ctypes.c_float * 6)()
+        info = (ctypes.c_uint64 * 5)()
+        self._check(self.lib.b200msm_last_timings(self._h, lane, ms, info))
+        d = {k: float(ms[i]) for i, k in enumerate(self.PHASES)}
+        d.update(window_bits=int(info[0]), windows=int(info[1]), entries=int(info[2]),
+                 accumulate_launches=int(info[3]), kernel_launches=int(info[4]))
+        return d
+
+    def microbench(self, kind, iters=4096):
+        g = ctypes.c_double()
+        self._check(self.lib.b200msm_microbench(self._h, kind, iters, ctypes.byref(g)))
+        return g.value
+
+    # ---- self-test hooks (tests only) --------------------------------------------------------
+    def selftest_field(self, group, op, a, b=None):
+        a = np.ascontiguousarray(a, dtype=np.uint64)
+        n = a.size // (12 * degree(self.curve, group))
+        out = np.zeros_like(a)
+        self._check(self.lib.b200msm_selftest_field(self._h, group, op, n, a.ctypes.data, _ptr(b), out.ctypes.data))
+        return out
+
+    def selftest_point(self, group, op, acc, q=None, flags=None):
+        acc = np.ascontiguousarray(acc, dtype=np.uint64)
+        n = acc.size // (36 * degree(self.curve, group))
+        out = np.zeros_like(acc)
+        if flags is not None:
+            flags = np.ascontiguousarray(flags, dtype=np.uint32)
+        self._check(self.lib.b200msm_selftest_point(self._h, group, op, n, acc.ctypes.data, _ptr(q), _ptr(flags), out.ctypes.data))
+        return out

@@ -1,0 +1,104 @@
+/* b200_msm.h -- C ABI of the B200-native MNT4753/MNT6753 multi-scalar-multiplication engine.
+ *
+ * This is the drop-in boundary for the MSM path of vezenovm/gpu-groth16-prover-3x.  Every entry
+ * point takes plain pointers and sizes in the reference's own wire format
+ * (libsnark/serialization.hpp:24-121, multiexp/reduce.cu:131-152):
+ *
+ *   scalar   12 x u64 little-endian limbs, Montgomery form of Fr (R = 2^768)
+ *   base     affine x || y, each coordinate DEG x 12 limbs Montgomery; infinity <=> y == 0
+ *            (DEG = 1 for G1, 2 for MNT4753 G2, 3 for MNT6753 G2)
+ *   result   Jacobian X || Y || Z (3 * DEG * 12 limbs), infinity <=> Z == 0, reported as (1,1,0);
+ *            it is what B::read_pt_ECp / read_pt_ECpe (prover_reference_functions.cpp:795-817)
+ *            already consume.
+ *
+ * There is no CPU fallback behind any of these symbols: without a usable CUDA device they fail
+ * with B200MSM_ERR_CUDA and never produce a point.
+ */
+#ifndef B200_MSM_H
+#define B200_MSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MSM_MNT4753 0
+#define B200MSM_MNT6753 1
+#define B200MSM_G1 1
+#define B200MSM_G2 2
+
+#define B200MSM_OK 0
+#define B200MSM_ERR_ARG 1
+#define B200MSM_ERR_CUDA 2
+#define B200MSM_ERR_OOM 3
+
+typedef struct b200msm_ctx b200msm_ctx;
+
+/* One context per (curve, GPU).  Replaces the implicit global state of cuda_prover_piecewise.cu
+ * (cudaMallocManaged buffers + streams created inside ec_reduce_straus, reduce.cu:135,198-209). */
+int b200msm_create(int curve, int device, b200msm_ctx **out);
+void b200msm_destroy(b200msm_ctx *ctx);
+/* Human-readable description of the last failure on this context (never NULL). */
+const char *b200msm_last_error(const b200msm_ctx *ctx);
+
+/* Upload a base set (A, B1, L, H queries: group G1; B2 query: group G2) and keep it resident in
+ * HBM.  Replaces load_points_affine<EC>(31 * n, preprocessed_file) (reduce.cu:254-271,
+ * cuda_prover_piecewise.cu:132-139): no 31x multiples table, no preprocessing file.
+ * `affine` may be a host or device pointer.  Returns a slot id >= 0 in *slot. */
+int b200msm_bases_upload(b200msm_ctx *ctx, int group, const uint64_t *affine, size_t n, int *slot);
+int b200msm_bases_free(b200msm_ctx *ctx, int slot);
+
+/* result = sum_{i<n} scalars[i] * bases[offset + i] over the resident base set `slot`.
+ * Replaces ec_reduce_straus<EC,C,R>(strm, out, multiples, scalars, N) (reduce.cu:131-152) and,
+ * through the host adaptor in INTEGRATION.md, B::multiexp_G1 / multiexp_G2
+ * (prover_reference_functions.cpp:350-368, 690-708).
+ * `scalars_mont` may be host (pageable or pinned) or device memory; `out_xyz` is host memory.
+ * The _async form enqueues on internal stream `lane` (0..3, the reference used one CUDA stream per
+ * MSM as a future: cuda_prover_piecewise.cu:162-167,187-193) and returns immediately; the result
+ * is valid after b200msm_wait(ctx, lane). */
+int b200msm_msm(b200msm_ctx *ctx, int slot, size_t offset, const uint64_t *scalars_mont, size_t n, uint64_t *out_xyz);
+int b200msm_msm_async(b200msm_ctx *ctx, int lane, int slot, size_t offset, const uint64_t *scalars_mont, size_t n,
+                      uint64_t *out_xyz);
+int b200msm_wait(b200msm_ctx *ctx, int lane);
+
+/* Literal counterpart of ec_reduce_straus: bases are passed with the call (host or device
+ * pointer, n affine points -- NOT the 31n-point multiples table) and uploaded inside the call. */
+int b200msm_ec_reduce(b200msm_ctx *ctx, int group, const uint64_t *bases_affine, const uint64_t *scalars_mont,
+                      size_t n, uint64_t *out_xyz);
+
+/* Multi-GPU: an MSM shards by point range (one context per GPU, each returns one partial Jacobian
+ * point); this folds n partials into one point on this context's GPU.  The reference has no
+ * multi-GPU path; inside the reference the same fold is G - 1 libff additions after read_pt_*. */
+int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size_t n, uint64_t *out_xyz);
+
+/* Tuning / introspection. */
+int b200msm_set_window_bits(b200msm_ctx *ctx, int c); /* 0 = automatic */
+/* Device time of the phases of the most recent completed MSM on `lane`, milliseconds, measured with
+ * CUDA events on the launching stream: [0] total, [1] H2D scalars, [2] recode+sort,
+ * [3] bucket accumulation (k_accumulate), [4] bucket reduction + window combine, [5] D2H result.
+ * info[0] = window bits c, [1] = windows W, [2] = sorted entries, [3] = k_accumulate launches (1),
+ * [4] = total kernel launches of the MSM. */
+int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[5]);
+
+/* Synthetic microbenchmarks used by bench.py for the roofline denominator: runs `iters`
+ * dependent-chain iterations of the named instruction mix on every SM and returns the achieved
+ * rate in 10^9 operations per second (a 32x32->64 multiply-accumulate counts as one operation).
+ * kind: 0 = IMAD.WIDE.U32 carry chains (the MSM's instruction), 1 = IMAD (mad.lo) only,
+ *       2 = the engine's own Fq Montgomery multiplication (returns 10^9 modmul/s). */
+int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops);
+
+/* Self-test hooks (used by tests/ only): the device field / point layer applied elementwise.
+ * field op: 0 mul, 1 add, 2 sub, 3 sqr, 5 neg, 6 mul_by_curve_a, 7 in-place mul, 8 dbl; elements are
+ * Fq for G1 and Fqe for G2 (DEG x 12 limbs).  point op: 0 acc += affine q (flags bit0: negate q,
+ * bit1: acc is infinity), 1 acc += jacobian q, 2 acc = 2*acc; acc / out are Jacobian X||Y||Z. */
+int b200msm_selftest_field(b200msm_ctx *ctx, int group, int op, size_t n, const uint64_t *a, const uint64_t *b,
+                           uint64_t *out);
+int b200msm_selftest_point(b200msm_ctx *ctx, int group, int op, size_t n, const uint64_t *acc, const uint64_t *q,
+                           const uint32_t *flags, uint64_t *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

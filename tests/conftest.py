@@ -1,0 +1,72 @@
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run on the GPU box with -m gpu)")
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for it in items:
+        if "gpu" in it.keywords:
+            it.add_marker(skip)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import pyoracle as po
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        env = dict(os.environ, CC="/usr/bin/gcc")
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "oracle"], check=True, env=env)
+    return po.load_oracle()
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return {name: np.load(os.path.join(GOLD, name + ".npz")) for name in
+            ("field_vectors", "point_vectors", "msm_vectors", "generators")}
+
+
+@pytest.fixture(scope="session")
+def emu():
+    """The device field/curve templates compiled for the host (tests/host_emu)."""
+    import ctypes
+    d = os.path.join(ROOT, "tests", "host_emu")
+    so = os.path.join(d, "libemu.so")
+    srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f)
+                                            for f in ("prim.cuh", "fq.cuh", "fe.cuh", "ec.cuh", "curves.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU", "-x", "c++",
+                        srcs[0], "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    lib.emu_field_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, u64p]
+    lib.emu_point_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p, u64p, ctypes.c_int, u64p]
+    lib.emu_fr_from_mont.argtypes = [ctypes.c_int, ctypes.c_size_t, u64p, u64p]
+    return lib
+
+
+@pytest.fixture(scope="session")
+def engine_lib():
+    import gpu_groth16_prover_3x_b200 as pkg
+    return pkg.load_library()

@@ -1,0 +1,56 @@
+"""The C-ABI library loads and exports every symbol include/b200_msm.h declares (no compute here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+import gpu_groth16_prover_3x_b200 as pkg
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200_msm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200msm_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(engine_lib):
+    syms = declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(engine_lib, s), "libb200msm.so does not export %s" % s
+
+
+def test_no_oracle_in_product():
+    """The product path never touches oracle/ (no import, no dlopen, no link)."""
+    pk = os.path.join(ROOT, "gpu_groth16_prover_3x_b200")
+    for dirpath, _, files in os.walk(pk):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "pyoracle" not in src and "liboracle" not in src and "libref" not in src, f
+    import subprocess
+    out = subprocess.run(["ldd", pkg.library_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libref" not in out
+
+
+def test_shard_ranges():
+    for n in (0, 1, 7, 8, 9, 1 << 20, (1 << 20) + 1):
+        for parts in (1, 2, 4, 8):
+            r = pkg.shard_ranges(n, parts)
+            assert len(r) == parts and sum(l for _, l in r) == n
+            assert all(r[i][0] + r[i][1] == r[i + 1][0] for i in range(parts - 1)) and r[0][0] == 0
+            assert max(l for _, l in r) - min(l for _, l in r) <= 1
+
+
+def test_create_fails_loudly_without_gpu(engine_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.MsmError) as e:
+        pkg.MsmContext(pkg.MNT4753, 0)
+    assert e.value.code == 2
+    h = ctypes.c_void_p()
+    assert engine_lib.b200msm_create(7, 0, ctypes.byref(h)) == 1  # bad curve id

@@ -1,0 +1,171 @@
+"""GPU parity of the MSM engine, through the C ABI, against (1) the golden vectors produced by the
+reference's libff, (2) the oracle on seeded inputs, (3) size-independent properties at full size."""
+import numpy as np
+import pytest
+
+import gpu_groth16_prover_3x_b200 as pkg
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+CG = [(c, g) for c in (0, 1) for g in (1, 2)]
+SIZES = (0, 1, 2, 31, 32, 33, 100, 257)
+
+
+@pytest.fixture(scope="module")
+def ctxs():
+    d = {c: pkg.MsmContext(c, 0) for c in (0, 1)}
+    yield d
+    for c in d.values():
+        c.close()
+
+
+def affine(oracle, curve, group, xyz):
+    return oracle.jacobian_to_affine(curve, group, xyz)
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_golden_vectors(ctxs, oracle, golden, curve, group):
+    """Edge cases planted in the fixtures: infinity bases, duplicate bases with equal scalars (P+P in a
+    bucket), P and -P with equal scalars, scalars 0, 1, 2, r-1, 2^15, 2^16-1, 2^16, 2^752."""
+    z = golden["msm_vectors"]
+    key = "c%d_g%d" % (curve, group)
+    deg = po.degree(curve, group)
+    bases, sc = z[key + "_bases"], z[key + "_scalars"]
+    ctx = ctxs[curve]
+    slot = ctx.upload_bases(group, bases)
+    try:
+        for c in (0, 2, 5, 8, 13, 16):
+            ctx.set_window_bits(c)
+            for n in SIZES:
+                got = affine(oracle, curve, group, ctx.msm(slot, sc[:n * 12], n))
+                assert (got == z["%s_n%d_out" % (key, n)]).all(), (c, n)
+        ctx.set_window_bits(0)
+        # sub-ranges of a resident base set (the L query uses scalars w[2..], cuda_prover_piecewise.cu:167)
+        for off, n in ((1, 32), (5, 1), (40, 4), (200, 57)):
+            want, _ = oracle.msm(curve, group, bases[off * 24 * deg:(off + n) * 24 * deg], sc[off * 12:(off + n) * 12])
+            got = affine(oracle, curve, group, ctx.msm(slot, sc[off * 12:(off + n) * 12], n, offset=off))
+            assert (got == want).all(), (off, n)
+    finally:
+        ctx.set_window_bits(0)
+        ctx.free_bases(slot)
+    # literal ec_reduce form: bases travel with the call
+    got = affine(oracle, curve, group, ctx.ec_reduce(group, bases[:100 * 24 * deg], sc[:1200]))
+    assert (got == z["%s_n100_out" % key]).all()
+
+
+@pytest.mark.parametrize("curve,group,log_n", [(0, 1, 14), (0, 2, 12), (1, 1, 14), (1, 2, 11)])
+def test_seeded_vs_oracle(ctxs, oracle, curve, group, log_n):
+    n = (1 << log_n) + 1
+    bases = oracle.gen_bases(curve, group, n)
+    sc = po.gen_scalars(curve, n, 21 + log_n)
+    want, _ = oracle.msm(curve, group, bases, sc)
+    got = affine(oracle, curve, group, ctxs[curve].ec_reduce(group, bases, sc))
+    assert (got == want).all()
+    assert (oracle.msm_closed_form(curve, group, sc) == want).all()
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_degenerate_inputs(ctxs, oracle, curve, group):
+    """All-identical bases (multiexp_profile.cpp:24-30 style), all-equal scalars (one giant bucket per
+    window), all-zero scalars, all-infinity bases."""
+    deg = po.degree(curve, group)
+    w = 24 * deg
+    n = 3000
+    r = po.fr_modulus(curve)
+    ctx = ctxs[curve]
+    one_pt = oracle.gen_bases(curve, group, 1)
+    same = np.tile(one_pt, n)
+    sc = po.gen_scalars(curve, n, 77)
+    ssum = sum(po.limbs_to_int(x) * pow(po.R, -1, r) % r for x in oracle.fr_to_mont(curve, oracle.fr_from_mont(curve, sc)).reshape(n, 12)) % r
+    want = oracle.point_op(curve, group, 3, one_pt, k=po.int_to_limbs(ssum * po.R % r))
+    assert (affine(oracle, curve, group, ctx.ec_reduce(group, same, sc)) == want).all()
+    # equal scalars on distinct bases: every entry of a window lands in the same bucket
+    bases = oracle.gen_bases(curve, group, n)
+    k = 0x1234567 * (1 << 700) + 0xDEADBEEFCAFE
+    eq = np.tile(po.int_to_limbs(k * po.R % r), n)
+    want, _ = oracle.msm(curve, group, bases, eq)
+    assert (affine(oracle, curve, group, ctx.ec_reduce(group, bases, eq)) == want).all()
+    # all-zero scalars and all-infinity bases give infinity, reported as Z == 0
+    out = ctx.ec_reduce(group, bases, np.zeros(n * 12, np.uint64))
+    assert not out[24 * deg:].any() and not affine(oracle, curve, group, out).any()
+    out = ctx.ec_reduce(group, np.zeros(n * w, np.uint64), sc)
+    assert not out[24 * deg:].any()
+
+
+def test_async_lanes_and_shards(ctxs, oracle):
+    """Four MSMs in flight on four lanes (A, B1, L on G1; B2 on G2), then the point-range sharding
+    identity: the fold of per-shard partials equals the unsharded MSM."""
+    curve = 0
+    ctx = ctxs[curve]
+    n = 2000
+    b1 = oracle.gen_bases(curve, 1, n)
+    b2 = oracle.gen_bases(curve, 2, n)
+    sc = po.gen_scalars(curve, n, 5)
+    s1, s2 = ctx.upload_bases(1, b1), ctx.upload_bases(2, b2)
+    ctx.msm_async(0, s1, sc)
+    ctx.msm_async(1, s2, sc)
+    ctx.msm_async(2, s1, sc[24:], n - 2, offset=2)
+    ctx.msm_async(3, s1, sc[:12 * 100], 100)
+    outs = [ctx.wait(i) for i in range(4)]
+    assert (affine(oracle, curve, 1, outs[0]) == oracle.msm(curve, 1, b1, sc)[0]).all()
+    assert (affine(oracle, curve, 2, outs[1]) == oracle.msm(curve, 2, b2, sc)[0]).all()
+    assert (affine(oracle, curve, 1, outs[2]) == oracle.msm(curve, 1, b1[48:], sc[24:])[0]).all()
+    assert (affine(oracle, curve, 1, outs[3]) == oracle.msm(curve, 1, b1[:2400], sc[:1200])[0]).all()
+    for parts in (2, 3, 8):
+        partials = [ctx.msm(s2, sc[off * 12:(off + ln) * 12], ln, offset=off) for off, ln in pkg.shard_ranges(n, parts)]
+        folded = ctx.fold(2, np.concatenate(partials))
+        assert (affine(oracle, curve, 2, folded) == affine(oracle, curve, 2, outs[1])).all()
+        assert (oracle.fold_jacobian(curve, 2, np.concatenate(partials)) == affine(oracle, curve, 2, outs[1])).all()
+    ctx.free_bases(s1)
+    ctx.free_bases(s2)
+
+
+def test_errors(ctxs):
+    ctx = ctxs[0]
+    with pytest.raises(pkg.MsmError):
+        ctx.set_window_bits(25)
+    slot = ctx.upload_bases(1, np.zeros(24 * 4, np.uint64))
+    with pytest.raises(pkg.MsmError):
+        ctx.msm(slot, np.zeros(12 * 8, np.uint64), 8)  # more scalars than bases
+    ctx.free_bases(slot)
+    with pytest.raises(pkg.MsmError):
+        ctx.free_bases(slot)
+
+
+@pytest.mark.parametrize("curve,group,log_n", [(0, 1, 20), (1, 2, 17)])
+def test_full_size_properties(ctxs, oracle, curve, group, log_n):
+    """BASELINE sizes, where the CPU MSM takes minutes: closed form of the structured bases
+    (sum s_i (P0 + i Q) = (sum s_i) P0 + (sum i s_i) Q), linearity in the scalars, and independence of
+    the result from the window width."""
+    import torch
+    n = 1 << log_n
+    deg = po.degree(curve, group)
+    ctx = ctxs[curve]
+    p0, q = oracle.base_pair(curve, group)
+    bases = np.zeros(n * 24 * deg, np.uint64)
+    assert oracle._f("gen_bases")(curve, group, n, po._p(p0), po._p(q), po._p(bases)) == 0
+    # cheap 751-bit scalars (SHA512_rng in python would take minutes at this size)
+    rng = np.random.default_rng(7)
+    raw = rng.integers(0, 1 << 63, size=(n, 12), dtype=np.uint64)
+    raw[:, 11] &= np.uint64((1 << 47) - 1)  # < 2^751 < r: canonical Montgomery residues of *some* scalars
+    vals = raw.reshape(-1)
+    slot = ctx.upload_bases(group, bases)
+    want = oracle.msm_closed_form(curve, group, vals)
+    got = ctx.msm(slot, vals)
+    assert (affine(oracle, curve, group, got) == want).all()
+    t = ctx.last_timings()
+    assert t["kernel_launches"] > 0 and t["accumulate"] > 0
+    # window-width independence
+    ctx.set_window_bits(13)
+    assert (affine(oracle, curve, group, ctx.msm(slot, vals)) == want).all()
+    ctx.set_window_bits(0)
+    # linearity: MSM(a) + MSM(b) == MSM(a + b) with a + b reduced mod r (Montgomery form is linear)
+    half = n // 2
+    a, b = vals[:half * 12], vals[half * 12:half * 24]
+    ab = oracle.field_op(1 - curve, 0, 1, a.copy(), b.copy())  # Fr(curve) = Fq(other curve)
+    s = ctx.fold(group, np.concatenate([ctx.msm(slot, a, half), ctx.msm(slot, b, half)]))
+    assert (affine(oracle, curve, group, s) == affine(oracle, curve, group, ctx.msm(slot, ab, half))).all()
+    # scalars already resident in HBM (device pointer) give the same point
+    dev = torch.from_numpy(vals.view(np.int64)).cuda()
+    assert (affine(oracle, curve, group, ctx.msm(slot, dev, n)) == want).all()
+    ctx.free_bases(slot)

@@ -1,0 +1,128 @@
+"""The exact field / curve templates the kernels instantiate (csrc/fq.cuh, fe.cuh, ec.cuh), compiled
+for the host with the PTX carry-chain primitives emulated, checked against the oracle and the golden
+fixtures.  This is what can be verified about the device code on a machine without a GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import pyoracle as po
+
+CG = [(c, g) for c in (0, 1) for g in (1, 2)]
+_p = po._p
+
+
+def emu_field(emu, curve, group, op, a, b=None):
+    out = np.zeros_like(a)
+    n = a.size // (12 * po.degree(curve, group))
+    assert emu.emu_field_op(curve, group, op, n, _p(a), _p(b), _p(out)) == 0
+    return out
+
+
+def emu_point(emu, curve, group, op, acc, q, flags=0):
+    out = np.zeros_like(acc)
+    ret = emu.emu_point_op(curve, group, op, _p(np.ascontiguousarray(acc)), _p(np.ascontiguousarray(q)) if q is not None else None, flags, _p(out))
+    return out, ret
+
+
+def to_jac(curve, group, aff):
+    """affine wire point -> Jacobian with Z = 1 (infinity -> (1,1,0))."""
+    deg = po.degree(curve, group)
+    one = po.ints_to_array([po.R % po.fq_modulus(curve)] + [0] * (deg - 1))
+    y = aff[12 * deg:]
+    if not y.any():
+        return np.concatenate([one, one, np.zeros(12 * deg, np.uint64)])
+    return np.concatenate([aff, one])
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_emu_field_golden(emu, golden, curve, group):
+    z = golden["field_vectors"]
+    key = "c%d_f%d" % (curve, 0 if group == 1 else 1)
+    a, b = z[key + "_a"], z[key + "_b"]
+    for op, name in ((0, "mul"), (1, "add"), (2, "sub"), (3, "sqr"), (5, "neg"), (7, "mul")):
+        got = emu_field(emu, curve, group, op, a, b)
+        assert (got == z["%s_%s_out" % (key, name)]).all(), name
+    dbl = emu_field(emu, curve, group, 8, a)
+    add = emu_field(emu, curve, group, 1, a, a)
+    assert (dbl == add).all()
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_emu_field_random(emu, oracle, curve, group):
+    rng = np.random.default_rng(curve * 10 + group)
+    p = po.fq_modulus(curve)
+    deg = po.degree(curve, group)
+    n = 300
+    a = po.ints_to_array([int.from_bytes(rng.bytes(100), "little") % p for _ in range(n * deg)])
+    b = po.ints_to_array([int.from_bytes(rng.bytes(100), "little") % p for _ in range(n * deg)])
+    f = 0 if group == 1 else 1
+    for op in (0, 1, 2, 3, 5):
+        assert (emu_field(emu, curve, group, op, a, b) == oracle.field_op(curve, f, op, a, b)).all(), op
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_emu_from_mont(emu, golden, curve):
+    z = golden["field_vectors"]
+    s = z["c%d_fr_mont" % curve]
+    out = np.zeros_like(s)
+    emu.emu_fr_from_mont(curve, s.size // 12, _p(s), _p(out))
+    assert (out == z["c%d_fr_plain_out" % curve]).all()
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_emu_point_ops(emu, oracle, golden, curve, group):
+    z = golden["point_vectors"]
+    key = "c%d_g%d" % (curve, group)
+    deg = po.degree(curve, group)
+    w = 24 * deg
+    A, B = z[key + "_a"].reshape(-1, w), z[key + "_b"].reshape(-1, w)
+    add_out, dbl_out = z[key + "_add_out"].reshape(-1, w), z[key + "_dbl_out"].reshape(-1, w)
+    for i in range(A.shape[0]):
+        ja, jb = to_jac(curve, group, A[i]), to_jac(curve, group, B[i])
+        # full Jacobian add
+        out, _ = emu_point(emu, curve, group, 1, ja, jb)
+        assert (oracle.jacobian_to_affine(curve, group, out) == add_out[i]).all(), ("add", i)
+        # doubling
+        out, _ = emu_point(emu, curve, group, 2, ja, None)
+        assert (oracle.jacobian_to_affine(curve, group, out) == dbl_out[i]).all(), ("dbl", i)
+        # mixed add (affine operand must not be infinity: the accumulate kernel never feeds one)
+        if B[i][12 * deg:].any():
+            a_inf = not A[i][12 * deg:].any()
+            out, _ = emu_point(emu, curve, group, 0, ja, B[i], 2 if a_inf else 0)
+            assert (oracle.jacobian_to_affine(curve, group, out) == add_out[i]).all(), ("madd", i)
+            # negated operand: A - B
+            negb = oracle.point_op(curve, group, 4, B[i])
+            want = oracle.point_op(curve, group, 0, A[i], negb)
+            out, _ = emu_point(emu, curve, group, 0, ja, B[i], (2 if a_inf else 0) | 1)
+            assert (oracle.jacobian_to_affine(curve, group, out) == want).all(), ("msub", i)
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_emu_point_chain_random_z(emu, oracle, curve, group):
+    """Accumulate 10 points with madd, then add the accumulator to itself and to its negation:
+    exercises Z != 1 operands in add / dbl and the P+P, P+(-P) branches."""
+    deg = po.degree(curve, group)
+    w = 24 * deg
+    pts = oracle.gen_bases(curve, group, 10).reshape(10, w)
+    acc = to_jac(curve, group, np.zeros(w, np.uint64))
+    want = np.zeros(w, np.uint64)
+    inf = 2
+    for i in range(10):
+        acc, r = emu_point(emu, curve, group, 0, acc, pts[i], inf)
+        inf = 2 if r else 0
+        want = oracle.point_op(curve, group, 0, want, pts[i])
+    assert (oracle.jacobian_to_affine(curve, group, acc) == want).all()
+    out, _ = emu_point(emu, curve, group, 1, acc, acc)      # P + P through the add path
+    assert (oracle.jacobian_to_affine(curve, group, out) == oracle.point_op(curve, group, 1, want)).all()
+    # P + (-P): negate Y of the Jacobian accumulator via the oracle field op
+    f = 0 if group == 1 else 1
+    neg = acc.copy()
+    neg[12 * deg:24 * deg] = oracle.field_op(curve, f, 5, acc[12 * deg:24 * deg].copy())
+    out, _ = emu_point(emu, curve, group, 1, acc, neg)
+    assert not oracle.jacobian_to_affine(curve, group, out).any()
+    # madd hitting P + P and P + (-P)
+    out, r = emu_point(emu, curve, group, 0, to_jac(curve, group, pts[3]), pts[3], 0)
+    assert (oracle.jacobian_to_affine(curve, group, out) == oracle.point_op(curve, group, 1, pts[3])).all() and r == 0
+    out, r = emu_point(emu, curve, group, 0, to_jac(curve, group, pts[3]), pts[3], 1)
+    assert r == 1 and not oracle.jacobian_to_affine(curve, group, out).any()
