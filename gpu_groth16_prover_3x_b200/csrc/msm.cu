@@ -138,6 +138,13 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, int c, char *base) {
     a.buckets = (uint32_t *)take((size_t)a.K * JACB);
     a.edges = (uint32_t *)take((size_t)a.max_chunks * 2 * JACB);
     a.edge_bucket = (uint32_t *)take((size_t)a.max_chunks * 2 * 4);
+    {
+        const size_t n1 = (a.max_chunks + FOLD_GS - 1) / FOLD_GS, n2 = (n1 + FOLD_GS - 1) / FOLD_GS;
+        a.fold_pts[0] = (uint32_t *)take(n1 * 2 * JACB);
+        a.fold_key[0] = (uint32_t *)take(n1 * 2 * 4);
+        a.fold_pts[1] = (uint32_t *)take(n2 * 2 * JACB);
+        a.fold_key[1] = (uint32_t *)take(n2 * 2 * 4);
+    }
     a.segsum = (uint32_t *)take((size_t)a.W * a.nseg * JACB);
     const size_t lvl = (size_t)a.W * ((a.nseg + 31) / 32) * JACB;
     a.tmp_a = (uint32_t *)take(lvl);
@@ -204,7 +211,7 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     a.base_inf = bs.inf + offset;
 
     if ((rc = set_smem(ctx, k_accumulate<G>, AC::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_fixup<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_fold_edges<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_bucket_reduce<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_sum<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_horner<G>, TC::TS::SMEM))) return rc;
@@ -226,14 +233,31 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     CU(cudaEventRecord(ln.ev[2], st));
 
     CU(cudaMemsetAsync(a.group_counter, 0, 4, st));
+    CU(cudaMemsetAsync(a.edge_bucket, 0xff, (size_t)a.max_chunks * 2 * 4, st));
     k_accumulate<G><<<ctx->sm_count * AC::MINB, AC::TS::THREADS, AC::TS::SMEM, st>>>(a);
     launches += 1;
     CU(cudaEventRecord(ln.ev[3], st));
 
     const unsigned tail_lanes = TC::TPB * 32;
-    k_fixup<G><<<(a.max_chunks + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
+    {
+        const uint32_t *in_pts = a.edges, *in_key = a.edge_bucket;
+        uint32_t n_in = a.max_chunks;
+        unsigned long long span = a.L;
+        int flip = 0;
+        do {
+            const uint32_t n_out = (n_in + FOLD_GS - 1) / FOLD_GS;
+            span *= FOLD_GS;
+            k_fold_edges<G><<<(n_out + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(
+                a, in_pts, in_key, n_in, a.fold_pts[flip], a.fold_key[flip], n_out, span);
+            ++launches;
+            in_pts = a.fold_pts[flip];
+            in_key = a.fold_key[flip];
+            n_in = n_out;
+            flip ^= 1;
+        } while (n_in > 1);
+    }
     k_bucket_reduce<G><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
-    launches += 2;
+    launches += 1;
     {
         const uint32_t *in = a.segsum;
         uint32_t nin = a.nseg;

@@ -10,7 +10,7 @@
 //                     streaming affine bases from HBM (128-bit cp.async into the team slab), one
 //                     mixed addition per entry; runs that cover a whole bucket are written straight
 //                     to the bucket array, runs cut by a chunk border go to an edge list
-//   k_fixup           folds edge partial sums of buckets that span several chunks
+//   k_fold_edges      hierarchical (32-ary) fold of the edge partial sums of buckets that span chunks
 //   k_bucket_reduce   per (window, segment): running-sum reduction  sum_b b*B_b  of a bucket segment
 //   k_sum             plain segmented sums (segment sums -> window sums)
 //   k_horner          window combine: result = sum_w 2^(c*w) * S_w
@@ -46,7 +46,9 @@ struct MsmArgs {
     uint32_t *entries;          // n * W : point index | sign << 31
     uint32_t *buckets;          // K Jacobian points (3*DEG*24 words each)
     uint32_t *edges;            // max_chunks * 2 Jacobian points
-    uint32_t *edge_bucket;      // max_chunks * 2
+    uint32_t *edge_bucket;      // max_chunks * 2, preset to EDGE_NONE by the host
+    uint32_t *fold_pts[2];      // ping-pong edge arrays of the fold levels
+    uint32_t *fold_key[2];
     uint32_t *segsum;           // W * nseg Jacobian points
     uint32_t *tmp_a, *tmp_b;    // scratch point arrays for k_sum levels
     uint32_t *winsum;           // W Jacobian points
@@ -294,7 +296,6 @@ __global__ void __launch_bounds__(AccCfg<G>::TS::THREADS, AccCfg<G>::MINB) k_acc
             b = bucket_of(a.offs, a.K, cstart);
             bstart = a.offs[b];
             bend = a.offs[b + 1];
-            if (T.comp == 0) { a.edge_bucket[2 * chunk] = EDGE_NONE; a.edge_bucket[2 * chunk + 1] = EDGE_NONE; }
         }
         bool acc_inf = true;
         bool neg_next = false;
@@ -357,9 +358,19 @@ struct TailCfg {
     typedef TeamSetup<G, NSLOT, TPB> TS;
 };
 
-// fold edge partials: lane = chunk whose edge[1] starts a chain
+// Hierarchical fold of the edge partials.  Level l >= 1 group g covers the sorted-list range
+// [g*span, (g+1)*span) with span = L * FOLD_GS^l; its inputs are the (at most two per child) edge
+// partials that its FOLD_GS children of level l-1 emitted, visited in list order so that all
+// partials of one bucket are consecutive.  One lane per group: runs of equal bucket id are summed;
+// a run whose bucket lies entirely inside the group is final (-> bucket array), otherwise it is
+// re-emitted as this group's own prefix (slot 0) / suffix (slot 1) edge for the next level.  The
+// depth is log_32(#chunks) and no lane ever walks more than 2*FOLD_GS partials, whatever the bucket
+// occupancy (a uniform scalar always has a giant top-window bucket: r ~ 1.77 * 2^752).
+constexpr uint32_t FOLD_GS = 32;
 template <class G>
-__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_fixup(MsmArgs a) {
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_fold_edges(MsmArgs a, const uint32_t *in_pts, const uint32_t *in_key,
+                                                                        uint32_t n_in, uint32_t *out_pts, uint32_t *out_key,
+                                                                        uint32_t n_out, unsigned long long span) {
     typedef typename G::F F;
     typedef TailCfg<G> C;
     constexpr int JACW = 3 * F::DEG * NLIMB;
@@ -369,26 +380,36 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_fixup(MsmArgs a) {
     const Team<F> T = C::TS::make(smem, s_flags, team);
     const int lane = threadIdx.x & 31;
     const PtSlots s = {0, 1, 2, 6, 7, 8, 9, 10, 11};
-    const uint32_t E = a.offs[a.K];
-    const uint32_t nchunks = (uint32_t)(((uint64_t)E + a.L - 1) / a.L);
-    const uint32_t chunk = (blockIdx.x * C::TPB + team) * 32 + lane;
-    uint32_t b = EDGE_NONE;
-    if (chunk < nchunks) b = a.edge_bucket[2 * chunk + 1];
-    bool head = b != EDGE_NONE;
-    if (!team_any(head)) return;
-    load_jac(T, s.X1, s.Y1, s.Z1, a.edges + ((size_t)chunk * 2 + 1) * JACW, head);
-    T.set_zero(s.Z1, !head);
-    uint32_t j = chunk + 1;
-    bool going = head;
-    for (;;) {
-        const bool cont = going && j < nchunks && a.edge_bucket[2 * j] == b;
-        if (!team_any(cont)) break;
-        load_jac(T, s.X2, s.Y2, s.Z2, a.edges + (size_t)j * 2 * JACW, cont);
-        T.set_zero(s.Z2, !cont);
-        Ec<F>::add(T, s, cont);
-        if (cont) ++j; else going = false;
+    const uint32_t g = (blockIdx.x * C::TPB + team) * 32 + lane;
+    const bool valid = g < n_out;
+    const unsigned long long E = a.offs[a.K];
+    const unsigned long long gstart = (unsigned long long)g * span, gend = min(gstart + span, E);
+    if (valid && T.comp == 0) { out_key[2 * g] = EDGE_NONE; out_key[2 * g + 1] = EDGE_NONE; }
+    uint32_t cur = EDGE_NONE;
+    auto flush = [&](bool pred) {
+        const uint32_t b = pred ? cur : 0u;
+        const uint32_t bstart = a.offs[b], bend = a.offs[b + 1];
+        const bool complete = bstart >= gstart && bend <= gend;
+        const uint32_t which = bstart < gstart ? 0u : 1u;
+        uint32_t *dst = complete ? a.buckets + (size_t)b * JACW : out_pts + ((size_t)g * 2 + which) * JACW;
+        if (pred && !complete && T.comp == 0) out_key[2 * g + which] = b;
+        store_jac(T, dst, s.X1, s.Y1, s.Z1, pred);
+    };
+    for (uint32_t i = 0; i < 2 * FOLD_GS; ++i) {
+        const uint32_t slot = (g * FOLD_GS) * 2 + i;
+        const uint32_t key = (valid && slot < 2 * n_in) ? in_key[slot] : EDGE_NONE;
+        const bool active = key != EDGE_NONE;
+        if (!team_any(active)) continue;
+        const bool newrun = active && key != cur;
+        const bool fl = newrun && cur != EDGE_NONE;
+        if (team_any(fl)) flush(fl);
+        T.set_zero(s.Z1, newrun);
+        if (newrun) cur = key;
+        load_jac(T, s.X2, s.Y2, s.Z2, in_pts + (size_t)slot * JACW, active);
+        T.set_zero(s.Z2, !active);
+        Ec<F>::add(T, s, active);
     }
-    store_jac(T, a.buckets + (size_t)b * JACW, s.X1, s.Y1, s.Z1, head);
+    flush(cur != EDGE_NONE);
 }
 
 // running-sum reduction of one bucket segment per lane; out[w*nseg + seg] = sum_{j<m} (seg*m+j+1) * B[w][seg*m+j]
