@@ -134,12 +134,18 @@ struct BQuads {
         if ((i & 3) == 0) cur[k] = p[k][(i >> 2) * stride];
         return (i & 3) == 0 ? cur[k].x : (i & 3) == 1 ? cur[k].y : (i & 3) == 2 ? cur[k].z : cur[k].w;
     }
+    MSM_DEVICE uint4 quad(int k, int q) const { return p[k][q * stride]; }
 };
 // K operands already in registers
 template <int K>
 struct BRegs {
     const uint32_t (*b)[NLIMB];
     MSM_DEVICE uint32_t get(int k, int i) const { return b[k][i]; }
+    MSM_DEVICE uint4 quad(int k, int q) const {
+        uint4 v;
+        v.x = b[k][4 * q]; v.y = b[k][4 * q + 1]; v.z = b[k][4 * q + 2]; v.w = b[k][4 * q + 3];
+        return v;
+    }
 };
 
 // r = (sum_{k<K} a[k] * b[k]) * R^-1 mod p, canonical.
@@ -231,6 +237,133 @@ MSM_DEVICE void fq_dot(fq_t &r, const uint32_t (&a)[K][NLIMB], BSrc &bsrc) {
     fq_cond_sub<M>(r, t);
 }
 
+// ---- reduced-radix dot product (EXPERIMENT, not used by the engine) ------------------------------
+// Same contract as fq_dot, different instruction mix: the product is evaluated in radix 2^W, W < 32,
+// so that every partial product is a carry-free IMAD.WIDE.U32 into a 64-bit column accumulator that
+// cannot overflow ((K+1) * N * 2^(2W) < 2^64); operands are re-sliced with funnel shifts on the ALU
+// pipe, the Montgomery digit of each row is m = T0 * (-p^-1) mod 2^W, columns are renormalised once
+// at the end and a last partial step of S = 768 - N*W bits completes the division by R = 2^768, so
+// results are bit-identical to the CIOS.  The idea was to escape the carry form IMAD.WIDE.U32.X.
+// Measured on B200 (b200msm_microbench kinds 2/3): it does not pay.  IMAD.WIDE.U32 with or
+// without carry issues on the half-rate "fmaheavy" sub-pipe (32 lanes/clk/SM), so the 1377 products of
+// this form (26^2 * 2 + 25) lose to the 1152 of the 32-bit CIOS: 5.5 vs 7.7 G modmul/s.  Kept for the
+// microbenchmark and the host-emulation parity test.
+//   K = 1 : W = 29, 26 limbs, S = 14        K = 2, 3 : W = 28, 27 (b, p) / 28 (scaled a) limbs, S = 12
+template <class M, int W>
+struct Radix {
+    static constexpr uint32_t MASK = (1u << W) - 1u;
+    MSM_HD static constexpr uint32_t P(int j) {
+        const int bit = W * j, w = bit >> 5, s = bit & 31;
+        const uint64_t lo = w < NLIMB ? (uint64_t)M::P(w) : 0ull;
+        const uint64_t hi = w + 1 < NLIMB ? (uint64_t)M::P(w + 1) : 0ull;
+        return (uint32_t)(((hi << 32) | lo) >> s) & MASK;
+    }
+};
+
+// W-bit limb j of a 768-bit little-endian word array (j is a compile-time constant after unrolling)
+template <int W>
+MSM_DEVICE uint32_t limb_of(const uint32_t (&x)[NLIMB], int j) {
+    const int bit = W * j, w = bit >> 5, s = bit & 31;
+    if (w >= NLIMB) return 0u;
+    uint32_t v = x[w] >> s;
+    if (s + W > 32 && w + 1 < NLIMB) v |= x[w + 1] << (32 - s);
+    return v & ((1u << W) - 1u);
+}
+
+template <class M, int K, class BSrc>
+MSM_DEVICE void fq_dot_rr(fq_t &r, const uint32_t (&a)[K][NLIMB], BSrc &bsrc) {
+    constexpr int W = (K == 1) ? 29 : 28;
+    constexpr int NB = (MNT753_NUM_BITS + W - 1) / W;      // limbs of a canonical operand and of p
+    constexpr int NA = (K == 1) ? NB : (768 + W - 1) / W;  // the a-operands of a tower product may be scaled by NR
+    constexpr int S = 768 - W * NB;
+    constexpr uint32_t MASK = (1u << W) - 1u;
+    typedef Radix<M, W> RX;
+    static_assert(S > 0 && S < 32, "leftover step");
+
+    uint32_t A[K][NA];
+#pragma unroll
+    for (int k = 0; k < K; ++k)
+#pragma unroll
+        for (int j = 0; j < NA; ++j) A[k][j] = limb_of<W>(a[k], j);
+
+    uint64_t T[NA];
+#pragma unroll
+    for (int j = 0; j < NA; ++j) T[j] = 0;
+    uint32_t bw[K][NLIMB];
+#pragma unroll
+    for (int i = 0; i < NB; ++i) {
+        // fetch the 128-bit quads of b that limb i reaches into and that are not here yet
+        const int hi_word = ((W * i + W - 1) >> 5) < NLIMB - 1 ? ((W * i + W - 1) >> 5) : NLIMB - 1;
+        const int prev_hi = i == 0 ? -1 : (((W * (i - 1) + W - 1) >> 5) < NLIMB - 1 ? ((W * (i - 1) + W - 1) >> 5) : NLIMB - 1);
+#pragma unroll
+        for (int q = 0; q < NLIMB / 4; ++q) {
+            if (4 * q <= hi_word && 4 * q > prev_hi) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) {
+                    const uint4 v = bsrc.quad(k, q);
+                    bw[k][4 * q] = v.x; bw[k][4 * q + 1] = v.y; bw[k][4 * q + 2] = v.z; bw[k][4 * q + 3] = v.w;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            const uint32_t bk = limb_of<W>(bw[k], i);
+#pragma unroll
+            for (int j = 0; j < NA; ++j) T[j] += (uint64_t)A[k][j] * bk;
+        }
+        const uint32_t m = prim::opaque(((uint32_t)T[0] * (M::INV & MASK)) & MASK);
+#pragma unroll
+        for (int j = 0; j < NB; ++j) T[j] += (uint64_t)m * RX::P(j);
+        const uint64_t c = T[0] >> W;
+#pragma unroll
+        for (int j = 0; j + 1 < NA; ++j) T[j] = T[j + 1];
+        T[NA - 1] = 0;
+        T[0] += c;
+    }
+
+    // renormalise the columns and repack into 32-bit words: t < 2^S * p + p < 2^768
+    uint32_t t[NLIMB + 2];
+    {
+        uint64_t acc = 0, c = 0;
+        int nbits = 0, wi = 0;
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            const uint64_t v = T[j] + c;
+            c = v >> W;
+            acc |= (uint64_t)((uint32_t)v & MASK) << nbits;
+            nbits += W;
+            if (nbits >= 32) {
+                if (wi < NLIMB) t[wi] = (uint32_t)acc;
+                ++wi;
+                acc >>= 32;
+                nbits -= 32;
+            }
+        }
+        acc |= c << nbits;
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            if (wi < NLIMB) t[wi] = (uint32_t)acc;
+            ++wi;
+            acc >>= 32;
+        }
+    }
+    // last S bits of the Montgomery division, in the 32-bit domain
+    const uint32_t m2 = (t[0] * M::INV) & ((1u << S) - 1u);
+    uint32_t u[NLIMB + 1];
+    uint64_t cy = 0;
+#pragma unroll
+    for (int j = 0; j < NLIMB; ++j) {
+        const uint64_t v = (uint64_t)m2 * M::P(j) + t[j] + cy;
+        u[j] = (uint32_t)v;
+        cy = v >> 32;
+    }
+    u[NLIMB] = (uint32_t)cy;
+    fq_t res;
+#pragma unroll
+    for (int j = 0; j < NLIMB; ++j) res[j] = (u[j] >> S) | (u[j + 1] << (32 - S));
+    fq_cond_sub<M>(r, res);
+}
+
 // plain Montgomery product of two register operands
 template <class M>
 MSM_DEVICE void fq_mul(fq_t &r, const fq_t &a, const fq_t &b) {
@@ -239,6 +372,15 @@ MSM_DEVICE void fq_mul(fq_t &r, const fq_t &a, const fq_t &b) {
     for (int i = 0; i < NLIMB; ++i) aa[0][i] = a[i];
     BRegs<1> src{reinterpret_cast<const uint32_t(*)[NLIMB]>(&b)};
     fq_dot<M, 1>(r, aa, src);
+}
+
+template <class M>
+MSM_DEVICE void fq_mul_rr(fq_t &r, const fq_t &a, const fq_t &b) {
+    uint32_t aa[1][NLIMB];
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) aa[0][i] = a[i];
+    BRegs<1> src{reinterpret_cast<const uint32_t(*)[NLIMB]>(&b)};
+    fq_dot_rr<M, 1>(r, aa, src);
 }
 
 // Montgomery -> plain integer (multiply by the integer 1), reference: Fr::from_monty, arith.cu:356-362

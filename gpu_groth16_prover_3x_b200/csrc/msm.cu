@@ -11,6 +11,7 @@
 
 #include "../../include/b200_msm.h"
 #include "msm_kernels.cuh"
+#include "util_kernels.cuh"
 
 using namespace mnt753;
 
@@ -28,7 +29,8 @@ struct BaseSet {
 };
 
 struct Lane {
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream MSMs are enqueued on
+    cudaStream_t own_stream = nullptr;  // the lane's internal stream (stream == own_stream unless overridden)
     cudaEvent_t ev[NEVENTS] = {};
     char *arena = nullptr;
     size_t arena_bytes = 0;
@@ -439,16 +441,126 @@ int run_fold(b200msm_ctx *ctx, const uint64_t *xyz, size_t n, uint64_t *out) {
     return B200MSM_OK;
 }
 
+// ---- affine normalisation / synthetic bases ---------------------------------------------------
+// exponent q^DEG - 2 of the Fermat inversion in Fq^DEG, little-endian 32-bit words
+template <class G>
+std::vector<uint32_t> fermat_exponent() {
+    constexpr int DEG = G::F::DEG;
+    std::vector<uint32_t> q(NLIMB), acc(1, 1u);
+    for (int i = 0; i < NLIMB; ++i) q[i] = G::F::M::P(i);
+    for (int d = 0; d < DEG; ++d) {
+        std::vector<uint32_t> r(acc.size() + NLIMB, 0u);
+        for (size_t i = 0; i < acc.size(); ++i) {
+            uint64_t carry = 0;
+            for (int j = 0; j < NLIMB; ++j) {
+                uint64_t t = (uint64_t)acc[i] * q[j] + r[i + j] + carry;
+                r[i + j] = (uint32_t)t;
+                carry = t >> 32;
+            }
+            r[i + NLIMB] = (uint32_t)carry;
+        }
+        acc.swap(r);
+    }
+    uint64_t borrow = 2;  // acc -= 2 (q is odd and > 2, so no underflow)
+    for (size_t i = 0; i < acc.size() && borrow; ++i) {
+        uint64_t t = (uint64_t)acc[i] - borrow;
+        acc[i] = (uint32_t)t;
+        borrow = (t >> 63) & 1u;
+    }
+    return acc;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+template <class G>
+int upload_exponent(b200msm_ctx *ctx, DevBuf &d, int &bits) {
+    std::vector<uint32_t> e = fermat_exponent<G>();
+    bits = G::F::DEG * MNT753_NUM_BITS;
+    CU(cudaMalloc(&d.p, e.size() * 4));
+    CU(cudaMemcpy(d.p, e.data(), e.size() * 4, cudaMemcpyHostToDevice));
+    return B200MSM_OK;
+}
+
+template <class G>
+int run_to_affine(b200msm_ctx *ctx, size_t n, const uint64_t *xyz, uint64_t *out) {
+    typedef TailCfg<G> TC;
+    constexpr size_t EB = G::F::DEG * NLIMB * 4;
+    DevBuf e, in, o;
+    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
+    if (rc) return rc;
+    CU(cudaMalloc(&in.p, n * 3 * EB));
+    CU(cudaMalloc(&o.p, n * 2 * EB));
+    CU(cudaMemcpy(in.p, xyz, n * 3 * EB, cudaMemcpyDefault));
+    CU(cudaFuncSetAttribute(k_to_affine<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    const unsigned lanes = TC::TPB * 32;
+    k_to_affine<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, (const uint32_t *)in.p, (uint32_t *)o.p,
+                                                                                         (const uint32_t *)e.p, bits);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, o.p, n * 2 * EB, cudaMemcpyDefault));
+    return B200MSM_OK;
+}
+
+template <class G>
+const uint32_t *generator_words() {
+    static const uint32_t c0g1[] = MNT753_GEN_C0_G1_U32, c0g2[] = MNT753_GEN_C0_G2_U32, c1g1[] = MNT753_GEN_C1_G1_U32,
+                          c1g2[] = MNT753_GEN_C1_G2_U32;
+    return G::CURVE == 0 ? (G::GROUP == 1 ? c0g1 : c0g2) : (G::GROUP == 1 ? c1g1 : c1g2);
+}
+
+// bases[i] = k_p0 * G + i * (k_q * G), written straight into a new resident base set
+template <class G>
+int run_synthetic(b200msm_ctx *ctx, size_t n, const uint64_t *k_p0, const uint64_t *k_q, BaseSet &bs) {
+    typedef TailCfg<G> TC;
+    constexpr size_t EB = G::F::DEG * NLIMB * 4;
+    constexpr uint32_t B = 64;
+    DevBuf e, gen, ks, pj, pa, jac, pre;
+    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
+    if (rc) return rc;
+    CU(cudaMalloc(&gen.p, 2 * EB));
+    CU(cudaMalloc(&ks.p, 2 * NLIMB * 4));
+    CU(cudaMalloc(&pj.p, 2 * 3 * EB));
+    CU(cudaMalloc(&pa.p, 2 * 2 * EB));
+    CU(cudaMalloc(&jac.p, n * 3 * EB));
+    CU(cudaMalloc(&pre.p, n * EB));
+    CU(cudaMemcpy(gen.p, generator_words<G>(), 2 * EB, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ks.p, k_p0, NLIMB * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy((uint32_t *)ks.p + NLIMB, k_q, NLIMB * 4, cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(k_scalar_mul<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    CU(cudaFuncSetAttribute(k_to_affine<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    CU(cudaFuncSetAttribute(k_synth_bases<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    for (int i = 0; i < 2; ++i)
+        k_scalar_mul<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>((const uint32_t *)gen.p, (const uint32_t *)ks.p + i * NLIMB,
+                                                             (uint32_t *)pj.p + i * 3 * (EB / 4));
+    k_to_affine<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>(2u, (const uint32_t *)pj.p, (uint32_t *)pa.p, (const uint32_t *)e.p, bits);
+    const unsigned lanes = TC::TPB * 32;
+    const size_t runs = (n + B - 1) / B;
+    k_synth_bases<G><<<(unsigned)((runs + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>(
+        (uint32_t)n, B, (const uint32_t *)pa.p, (const uint32_t *)pa.p + 2 * (EB / 4), bs.pts, (uint32_t *)jac.p, (uint32_t *)pre.p,
+        (const uint32_t *)e.p, bits);
+    constexpr int DEG = G::F::DEG;
+    k_flag_inf<DEG><<<(unsigned)((n + 255) / 256), 256>>>(bs.pts, (uint32_t)n, bs.inf);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return B200MSM_OK;
+}
+
 // ---- microbenchmarks ------------------------------------------------------------------------------
-constexpr int MB_CHAINS = 8;
+constexpr int MB_CHAINS = 16;
+// 16 independent chains per thread; the multiplier of every step is the low word of the chain's own
+// accumulator, so nothing is loop-invariant (an earlier version with constant multipliers was hoisted
+// by ptxas into 64-bit adds and reported twice the real rate).
 __global__ void __launch_bounds__(256) k_mb_wide(uint32_t *out, int iters) {
     uint64_t acc[MB_CHAINS];
     const uint32_t b = 0x9e3779b9u + blockIdx.x;
-    for (int j = 0; j < MB_CHAINS; ++j) acc[j] = (uint64_t)(threadIdx.x + 1) * (j + 3);
+    for (int j = 0; j < MB_CHAINS; ++j) acc[j] = (uint64_t)(threadIdx.x + 1) * (j + 3) + 0x100000001ull * j;
     for (int it = 0; it < iters; ++it) {
 #pragma unroll
         for (int j = 0; j < MB_CHAINS; ++j) {
-            const uint32_t m = (uint32_t)acc[(j + 1) % MB_CHAINS];
+            const uint32_t m = (uint32_t)acc[j];
             asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(m), "r"(b));
         }
     }
@@ -470,14 +582,16 @@ __global__ void __launch_bounds__(256) k_mb_lo(uint32_t *out, int iters) {
     if (s == 0x12345678u) out[0] = 1;
 }
 // the engine's own register-resident Montgomery product, iterated
-template <class M>
+template <class M, bool RR>
 __global__ void __launch_bounds__(128) k_mb_fqmul(uint32_t *out, int iters) {
     fq_t x, y;
 #pragma unroll
     for (int i = 0; i < NLIMB; ++i) { x[i] = M::R1(i) ^ (threadIdx.x * 7u + i); y[i] = M::R2(i) ^ (blockIdx.x + i); }
     x[NLIMB - 1] &= 0xffffu;
     y[NLIMB - 1] &= 0xffffu;
-    for (int it = 0; it < iters; ++it) fq_mul<M>(x, x, y);
+    for (int it = 0; it < iters; ++it) {
+        if (RR) fq_mul_rr<M>(x, x, y); else fq_mul<M>(x, x, y);
+    }
     uint32_t s = 0;
 #pragma unroll
     for (int i = 0; i < NLIMB; ++i) s ^= x[i];
@@ -505,7 +619,8 @@ int b200msm_create(int curve, int device, b200msm_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     for (int i = 0; i < NLANES; ++i) {
         Lane &ln = ctx->lanes[i];
-        bool ok = cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking) == cudaSuccess;
+        bool ok = cudaStreamCreateWithFlags(&ln.own_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ln.stream = ln.own_stream;
         for (int e = 0; e < NEVENTS && ok; ++e) ok = cudaEventCreate(&ln.ev[e]) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_result, 3 * 3 * NLIMB * 4) == cudaSuccess;
         if (!ok) { b200msm_destroy(ctx); return B200MSM_ERR_CUDA; }
@@ -523,7 +638,7 @@ void b200msm_destroy(b200msm_ctx *ctx) {
         if (ln.arena) cudaFree(ln.arena);
         if (ln.h_result) cudaFreeHost(ln.h_result);
         for (int e = 0; e < NEVENTS; ++e) if (ln.ev[e]) cudaEventDestroy(ln.ev[e]);
-        if (ln.stream) cudaStreamDestroy(ln.stream);
+        if (ln.own_stream) cudaStreamDestroy(ln.own_stream);
     }
     for (auto &s : ctx->sets) if (s.used) { cudaFree(s.pts); cudaFree(s.inf); }
     delete ctx;
@@ -621,6 +736,64 @@ int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size
     return group == B200MSM_G1 ? run_fold<Mnt6G1>(ctx, partials_xyz, n, out_xyz) : run_fold<Mnt6G2>(ctx, partials_xyz, n, out_xyz);
 }
 
+int b200msm_to_affine(b200msm_ctx *ctx, int group, size_t n, const uint64_t *xyz, uint64_t *out_affine) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!xyz || !out_affine || n == 0 || n > (1u << 24) || (group != B200MSM_G1 && group != B200MSM_G2))
+        return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->curve == B200MSM_MNT4753)
+        return group == B200MSM_G1 ? run_to_affine<Mnt4G1>(ctx, n, xyz, out_affine) : run_to_affine<Mnt4G2>(ctx, n, xyz, out_affine);
+    return group == B200MSM_G1 ? run_to_affine<Mnt6G1>(ctx, n, xyz, out_affine) : run_to_affine<Mnt6G2>(ctx, n, xyz, out_affine);
+}
+
+int b200msm_bases_synthetic(b200msm_ctx *ctx, int group, size_t n, const uint64_t *k_p0_mont, const uint64_t *k_q_mont, int *slot) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!slot || !k_p0_mont || !k_q_mont || n == 0 || n >= (size_t(1) << 31) || (group != B200MSM_G1 && group != B200MSM_G2))
+        return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    const int deg = degree_of(ctx->curve, group);
+    BaseSet bs;
+    bs.used = true;
+    bs.group = group;
+    bs.n = n;
+    CU(cudaMalloc(&bs.pts, n * 2 * deg * NLIMB * 4));
+    cudaError_t e = cudaMalloc(&bs.inf, n);
+    if (e != cudaSuccess) { cudaFree(bs.pts); return fail(ctx, B200MSM_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    int rc;
+    if (ctx->curve == B200MSM_MNT4753)
+        rc = group == B200MSM_G1 ? run_synthetic<Mnt4G1>(ctx, n, k_p0_mont, k_q_mont, bs) : run_synthetic<Mnt4G2>(ctx, n, k_p0_mont, k_q_mont, bs);
+    else
+        rc = group == B200MSM_G1 ? run_synthetic<Mnt6G1>(ctx, n, k_p0_mont, k_q_mont, bs) : run_synthetic<Mnt6G2>(ctx, n, k_p0_mont, k_q_mont, bs);
+    if (rc) { cudaFree(bs.pts); cudaFree(bs.inf); return rc; }
+    int id = -1;
+    for (size_t i = 0; i < ctx->sets.size(); ++i) if (!ctx->sets[i].used) { id = (int)i; break; }
+    if (id < 0) { ctx->sets.push_back(bs); id = (int)ctx->sets.size() - 1; } else ctx->sets[id] = bs;
+    *slot = id;
+    return B200MSM_OK;
+}
+
+int b200msm_bases_download(b200msm_ctx *ctx, int slot, size_t offset, size_t n, uint64_t *out_affine) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (slot < 0 || slot >= (int)ctx->sets.size() || !ctx->sets[slot].used) return fail(ctx, B200MSM_ERR_ARG, "bad base slot %d", slot);
+    const BaseSet &bs = ctx->sets[slot];
+    if (!out_affine || offset > bs.n || n > bs.n - offset) return fail(ctx, B200MSM_ERR_ARG, "bad range");
+    CU(cudaSetDevice(ctx->device));
+    const size_t pw = (size_t)2 * degree_of(ctx->curve, bs.group) * NLIMB;
+    CU(cudaMemcpy(out_affine, bs.pts + offset * pw, n * pw * 4, cudaMemcpyDefault));
+    return B200MSM_OK;
+}
+
+int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (lane < 0 || lane >= NLANES) return fail(ctx, B200MSM_ERR_ARG, "lane %d out of range", lane);
+    Lane &ln = ctx->lanes[lane];
+    if (ln.pending) return fail(ctx, B200MSM_ERR_ARG, "lane %d still has an un-waited MSM", lane);
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ln.stream));
+    ln.stream = cuda_stream ? (cudaStream_t)cuda_stream : ln.own_stream;
+    return B200MSM_OK;
+}
+
 int b200msm_set_window_bits(b200msm_ctx *ctx, int c) {
     if (!ctx) return B200MSM_ERR_ARG;
     if (c != 0 && (c < 2 || c > 20)) return fail(ctx, B200MSM_ERR_ARG, "window bits %d outside [2, 20]", c);
@@ -638,7 +811,7 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
 
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     if (!ctx) return B200MSM_ERR_ARG;
-    if (!gops || iters <= 0 || kind < 0 || kind > 2) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    if (!gops || iters <= 0 || kind < 0 || kind > 3) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     uint32_t *d = nullptr;
     CU(cudaMalloc(&d, 256));
@@ -652,8 +825,9 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
         if (kind == 0) { k_mb_wide<<<blocks, 256>>>(d, iters); ops = double(blocks) * 256 * iters * MB_CHAINS; }
         else if (kind == 1) { k_mb_lo<<<blocks, 256>>>(d, iters); ops = double(blocks) * 256 * iters * MB_CHAINS; }
         else {
-            if (ctx->curve == B200MSM_MNT4753) k_mb_fqmul<ModA><<<blocks, 128>>>(d, iters);
-            else k_mb_fqmul<ModB><<<blocks, 128>>>(d, iters);
+            if (kind == 3) k_mb_fqmul<ModA, true><<<blocks, 128>>>(d, iters);
+            else if (ctx->curve == B200MSM_MNT4753) k_mb_fqmul<ModA, false><<<blocks, 128>>>(d, iters);
+            else k_mb_fqmul<ModB, false><<<blocks, 128>>>(d, iters);
             ops = double(blocks) * 128 * iters;
         }
         CU(cudaEventRecord(e1, 0));

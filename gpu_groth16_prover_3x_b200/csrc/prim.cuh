@@ -30,6 +30,8 @@ inline uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(
 inline uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return add_cc(mul_hi(a, b), c); }
 inline uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { return addc_cc(mul_hi(a, b), c); }
 inline uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { return mul_hi(a, b) + c + cf; }
+inline uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) { return (uint64_t)a * b + c; }
+inline uint32_t opaque(uint32_t x) { return x; }
 }  // namespace prim
 #else
 #define MSM_HD __host__ __device__
@@ -49,5 +51,11 @@ MSM_DEVICE uint32_t madc_lo_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r;
 MSM_DEVICE uint32_t mad_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MSM_ASM("mad.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 MSM_DEVICE uint32_t madc_hi_cc(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MSM_ASM("madc.hi.cc.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 MSM_DEVICE uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) { uint32_t r; MSM_ASM("madc.hi.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+// carry-free 32x32+64 -> 64: one plain IMAD.WIDE.U32 (full-rate, unlike the .X carry form).  Not volatile:
+// it is pure arithmetic and ptxas is free to schedule it.
+MSM_DEVICE uint64_t mad_wide(uint32_t a, uint32_t b, uint64_t c) { uint64_t r; asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(r) : "r"(a), "r"(b), "l"(c)); return r; }
+// hides a compile-time constant from NVVM (which would turn u32 x const into a 64-bit multiply whose
+// high-word fix-up ptxas does not fold away); ptxas still propagates it into the immediate field.
+MSM_DEVICE uint32_t opaque(uint32_t x) { asm("" : "+r"(x)); return x; }
 }  // namespace prim
 #endif

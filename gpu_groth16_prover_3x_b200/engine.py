@@ -55,7 +55,11 @@ def load_library():
     lib.b200msm_msm_async.argtypes = [vp, ci, ci, sz, vp, sz, vp]
     lib.b200msm_wait.argtypes = [vp, ci]
     lib.b200msm_ec_reduce.argtypes = [vp, ci, vp, vp, sz, vp]
+    lib.b200msm_bases_synthetic.argtypes = [vp, ci, sz, vp, vp, ctypes.POINTER(ci)]
+    lib.b200msm_bases_download.argtypes = [vp, ci, sz, sz, vp]
+    lib.b200msm_to_affine.argtypes = [vp, ci, sz, vp, vp]
     lib.b200msm_fold.argtypes = [vp, ci, vp, sz, vp]
+    lib.b200msm_set_stream.argtypes = [vp, ci, vp]
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
     lib.b200msm_last_timings.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), _u64p]
     lib.b200msm_microbench.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double)]
@@ -144,6 +148,32 @@ class MsmContext:
         self._slot_group[slot.value] = (group, n)
         return slot.value
 
+    def synthetic_bases(self, group, n, k_p0_mont, k_q_mont):
+        """Resident base set P0 + i*Q, P0 = k_p0*G, Q = k_q*G, generated on the device."""
+        slot = ctypes.c_int(-1)
+        k0 = np.ascontiguousarray(k_p0_mont, dtype=np.uint64)
+        k1 = np.ascontiguousarray(k_q_mont, dtype=np.uint64)
+        assert k0.size == 12 and k1.size == 12
+        self._check(self.lib.b200msm_bases_synthetic(self._h, group, n, k0.ctypes.data, k1.ctypes.data, ctypes.byref(slot)))
+        self._slot_group[slot.value] = (group, n)
+        return slot.value
+
+    def download_bases(self, slot, offset=0, n=None):
+        group, nb = self._slot_group[slot]
+        if n is None:
+            n = nb - offset
+        out = np.zeros(n * 24 * degree(self.curve, group), np.uint64)
+        self._check(self.lib.b200msm_bases_download(self._h, slot, offset, n, out.ctypes.data))
+        return out
+
+    def to_affine(self, group, xyz):
+        """Jacobian X||Y||Z points -> affine wire format on the device (infinity -> zeros)."""
+        xyz = np.ascontiguousarray(xyz, dtype=np.uint64).reshape(-1)
+        n = xyz.size // (36 * degree(self.curve, group))
+        out = np.zeros(n * 24 * degree(self.curve, group), np.uint64)
+        self._check(self.lib.b200msm_to_affine(self._h, group, n, xyz.ctypes.data, out.ctypes.data))
+        return out
+
     def free_bases(self, slot):
         self._check(self.lib.b200msm_bases_free(self._h, slot))
         self._slot_group.pop(slot, None)
@@ -199,6 +229,10 @@ class MsmContext:
         return out
 
     # ---- tuning / introspection --------------------------------------------------------------
+    def set_stream(self, lane, cuda_stream):
+        """Run lane `lane` on a caller-owned CUDA stream (integer handle, e.g. torch Stream.cuda_stream); 0 = internal."""
+        self._check(self.lib.b200msm_set_stream(self._h, lane, ctypes.c_void_p(cuda_stream or None)))
+
     def set_window_bits(self, c):
         self._check(self.lib.b200msm_set_window_bits(self._h, c))
 

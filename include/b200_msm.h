@@ -68,10 +68,28 @@ int b200msm_wait(b200msm_ctx *ctx, int lane);
 int b200msm_ec_reduce(b200msm_ctx *ctx, int group, const uint64_t *bases_affine, const uint64_t *scalars_mont,
                       size_t n, uint64_t *out_xyz);
 
+/* Synthetic base set of SURVEY.md 8(d), generated in HBM: bases[i] = P0 + i*Q with P0 = k_p0 * G and
+ * Q = k_q * G (G = G1_one / G2_one of the curve; scalars in Montgomery form).  Its MSM has the closed
+ * form (sum s_i) P0 + (sum i s_i) Q.  b200msm_bases_download copies points of a resident set to
+ * host (or device) memory in the affine wire format. */
+int b200msm_bases_synthetic(b200msm_ctx *ctx, int group, size_t n, const uint64_t *k_p0_mont, const uint64_t *k_q_mont,
+                            int *slot);
+int b200msm_bases_download(b200msm_ctx *ctx, int slot, size_t offset, size_t n, uint64_t *out_affine);
+
+/* Affine normalisation of n Jacobian points on the device: (X/Z^2, Y/Z^3), infinity -> all-zero
+ * (the writer convention of libsnark/serialization.hpp:43-67).  The reference does this on the host
+ * with libff after read_pt_* (cuda_prover_piecewise.cu:187-204); its kernels have no inversion. */
+int b200msm_to_affine(b200msm_ctx *ctx, int group, size_t n, const uint64_t *xyz, uint64_t *out_affine);
+
 /* Multi-GPU: an MSM shards by point range (one context per GPU, each returns one partial Jacobian
  * point); this folds n partials into one point on this context's GPU.  The reference has no
  * multi-GPU path; inside the reference the same fold is G - 1 libff additions after read_pt_*. */
 int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size_t n, uint64_t *out_xyz);
+
+/* Enqueue lane `lane` on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the
+ * internal stream).  The reference hands a cudaStream_t& back to its caller for the same purpose
+ * (reduce.cu:131-135): ordering the MSM against the caller's own work and timing it with events. */
+int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream);
 
 /* Tuning / introspection. */
 int b200msm_set_window_bits(b200msm_ctx *ctx, int c); /* 0 = automatic */
@@ -86,7 +104,9 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
  * dependent-chain iterations of the named instruction mix on every SM and returns the achieved
  * rate in 10^9 operations per second (a 32x32->64 multiply-accumulate counts as one operation).
  * kind: 0 = IMAD.WIDE.U32 carry chains (the MSM's instruction), 1 = IMAD (mad.lo) only,
- *       2 = the engine's own Fq Montgomery multiplication (returns 10^9 modmul/s). */
+ *       2 = the engine's own Fq Montgomery multiplication (32-bit CIOS on IMAD.WIDE.U32.X carry
+ *           chains; returns 10^9 modmul/s),
+ *       3 = the reduced-radix (29-bit limbs, carry-free IMAD.WIDE.U32) experiment, for comparison. */
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops);
 
 /* Self-test hooks (used by tests/ only): the device field / point layer applied elementwise.

@@ -62,6 +62,7 @@ def emu():
     u64p = ctypes.POINTER(ctypes.c_uint64)
     lib.emu_field_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, u64p]
     lib.emu_point_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p, u64p, ctypes.c_int, u64p]
+    lib.emu_fq_mul.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, u64p]
     lib.emu_fr_from_mont.argtypes = [ctypes.c_int, ctypes.c_size_t, u64p, u64p]
     return lib
 

@@ -37,7 +37,7 @@ sc = raw.reshape(-1)
 print("inputs ready in %.1fs" % (time.time() - t0), flush=True)
 ctx = pkg.MsmContext(a.curve, 0)
 if a.micro:
-    for kind, name in ((0, "IMAD.WIDE GMAC/s"), (1, "IMAD.LO Gop/s"), (2, "Fq modmul G/s")):
+    for kind, name in ((0, "IMAD.WIDE GMAC/s"), (1, "IMAD.LO Gop/s"), (2, "Fq modmul G/s"), (3, "Fq modmul RR29 G/s")):
         print("microbench %-18s %.1f" % (name, ctx.microbench(kind, 2048)), flush=True)
 slot = ctx.upload_bases(a.group, bases)
 want = orc.msm_closed_form(a.curve, a.group, sc) if a.check else None
