@@ -181,6 +181,7 @@ def run_b200(args):
     t0 = time.perf_counter()
     slot = ctx.synthetic_bases(group, n, k0_rank, k1)
     t_bases = time.perf_counter() - t0
+    binfo = ctx.bases_info(slot)
 
     host_sets = [torch.from_numpy(synthetic.random_scalars(curve, n, 100 + 2 * rank + i).view(np.int64)).pin_memory() for i in range(2)]
     dev_sets = [h.cuda(non_blocking=False) for h in host_sets]
@@ -264,11 +265,18 @@ def run_b200(args):
     hbm_peak, hbm_src = measured_hbm_peak()
     aff_bytes = 2 * deg * 96
     alg_bytes = float(n) * W * (aff_bytes + 4)
+    # SURVEY.md 8(d) canonical count (c = 16, W = 48, Jacobian mixed add) applied to the whole step: what the
+    # reference-style algorithm would have to execute to deliver the same points/s
+    canonical_macs_per_point = 1176.0 * 11 * k_tower * 48
     roofline = {
         "kernel": "k_accumulate", "bound": "imad", "achieved": achieved, "peak": peak, "unit": "GMAC/s", "frac": achieved / peak,
         "traffic": None, "launch_ms": acc_ms, "share_of_step": acc_ms / (dev_s / args.steps * 1e3),
-        "peak_source": "measured in this run: max(IMAD.WIDE.U32 stream, Fq Montgomery product in registers x 1176 MAC)",
+        "peak_source": "measured in this run: max(IMAD.WIDE.U32 stream, Fq Montgomery product in registers x 1176 MAC); "
+                       "a 32x32->64 multiply-add issues at 32 per clock per SM on B200 (tools/pipe_probe.cu)",
         "macs_per_launch": macs_per_launch, "micro": micro,
+        "canonical_c16": {"macs_per_point": canonical_macs_per_point,
+                          "step_gmacs": total_points / world * args.steps / dev_s * canonical_macs_per_point / 1e9,
+                          "frac_of_peak": total_points / world * args.steps / dev_s * canonical_macs_per_point / 1e9 / peak},
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (acc_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": alg_bytes / (acc_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src},
     }
@@ -293,9 +301,11 @@ def run_b200(args):
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload_name(curve, group, args.log_n), "curve": CURVE_NAMES[curve], "group": "G%d" % group,
                    "points_per_gpu": n, "total_points": total_points, "window_bits": info["window_bits"], "windows": W,
+                   "bucket_sets": info["bucket_sets"], "window_tables": info["tables"], "table_bytes_per_gpu": binfo["bytes"],
+                   "table_build_s": binfo["table_build_ms"] / 1e3,
                    "sharding": "point-range, one partial point per GPU, no collective on the data path",
                    "cache": "inputs larger than L2 (bases %.0f MB + scalars %.0f MB + sorted list %.0f MB per step)" % (
-                       n * aff_bytes / 1e6, n * 96 / 1e6, n * W * 4 / 1e6),
+                       binfo["bytes"] / 1e6, n * 96 / 1e6, n * W * 4 / 1e6),
                    "timing": "CUDA events on the launching stream around the K steps, max over ranks",
                    "bases_generation_s": t_bases},
         "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n * 96, "d2h_bytes_per_step": 36 * deg * 8,

@@ -1,13 +1,24 @@
-"""Compile csrc/msm.cu into libb200msm.so for sm_100a (nvcc cross-compiles without a GPU)."""
+"""Compile csrc/*.cu into libb200msm.so for sm_100a (nvcc cross-compiles without a GPU).
+
+The four groups (MNT4753/MNT6753 x G1/G2) are instantiated in their own translation units
+(csrc/inst_*.cu) and compiled in parallel; msm.cu holds the C ABI.
+"""
+import concurrent.futures
 import os
 import shutil
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libb200msm.so")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared",
-              "-Xcompiler", "-fPIC"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+NVCC_FLAGS = ARCH + ["-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC"]
+HOST_CXX = "/usr/bin/g++"  # the image's default CXX is a relocated wrapper; use the system compiler
+
+
+def units():
+    return [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(".cu")]
 
 
 def sources():
@@ -30,8 +41,24 @@ def build(force=False, verbose=False):
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(nvcc):
         raise RuntimeError("nvcc not found: cannot build libb200msm.so")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB + ".tmp", os.path.join(CSRC, "msm.cu")]
-    subprocess.run(cmd, check=True, cwd=CSRC)
+    os.makedirs(OBJ, exist_ok=True)
+    ccbin = ["-ccbin", HOST_CXX] if os.path.exists(HOST_CXX) else []
+    extra = ["-Xptxas", "-v"] if verbose else []
+
+    def compile_one(src):
+        obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
+        r = subprocess.run([nvcc] + ccbin + NVCC_FLAGS + extra + ["-c", "-o", obj, src], cwd=CSRC, capture_output=True, text=True)
+        return src, obj, r
+
+    objs = []
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        for src, obj, r in ex.map(compile_one, units()):
+            if verbose or r.returncode:
+                print(r.stdout + r.stderr)
+            if r.returncode:
+                raise RuntimeError("nvcc failed on %s" % src)
+            objs.append(obj)
+    subprocess.run([nvcc] + ccbin + ARCH + ["-shared", "-o", LIB + ".tmp"] + objs, check=True, cwd=CSRC)
     os.replace(LIB + ".tmp", LIB)
     return LIB
 

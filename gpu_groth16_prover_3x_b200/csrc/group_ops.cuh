@@ -1,0 +1,493 @@
+// Per-group (curve x G1/G2) host routines: everything that launches a kernel templated on the group.
+// Each of the four groups is instantiated in its own translation unit (inst_*.cu) so that the library
+// builds in parallel; msm.cu reaches them through the GroupOps table.
+#pragma once
+#include "host_ctx.cuh"
+
+namespace {
+
+template <class G>
+Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) {
+    typedef AccCfg<G> AC;
+    constexpr size_t JACB = 3 * G::F::DEG * NLIMB * 4;
+    Plan p;
+    MsmArgs &a = p.a;
+    memset(&a, 0, sizeof a);
+    const int c = cfg.c;
+    a.n = (uint32_t)n;
+    a.c = c;
+    a.Wd = cfg.Wd;
+    a.W = cfg.G;
+    a.NB = 1u << (c - 1);
+    a.K = (uint32_t)a.W * a.NB;
+    const uint64_t emax = (uint64_t)n * a.Wd;
+    // lanes resident on the device in k_accumulate; aim at ~6 chunks per lane for load balance
+    const uint64_t lanes = (uint64_t)ctx->sm_count * AC::MINB * AC::TPB * 32;
+    uint64_t L = emax / (lanes * 6);
+    if (L < 8) L = 8;
+    if (L > 256) L = 256;
+    a.L = (uint32_t)L;
+    a.max_chunks = (uint32_t)((emax + L - 1) / L) + 1;
+    // bucket-reduce segment length: keep >= ~32k lanes of segments when there are that many buckets
+    uint32_t m = 1;
+    while ((uint64_t)a.K / (m * 2) >= 32768 && m * 2 <= a.NB && m < 64) m *= 2;
+    a.m = m;
+    a.nseg = a.NB / m;
+    p.nscan = (a.K + SCAN_B - 1) / SCAN_B;
+
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *q = base + off; off += align_up(bytes, 256); return q; };
+    a.scalars = (uint32_t *)take(n * NLIMB * 4);
+    a.count = (uint32_t *)take((size_t)a.K * 4);
+    a.offs = (uint32_t *)take(((size_t)a.K + 1) * 4);
+    a.cursor = (uint32_t *)take((size_t)a.K * 4);
+    p.bsum = (uint32_t *)take((size_t)p.nscan * 4);
+    a.group_counter = (uint32_t *)take(4);
+    a.entries = (uint32_t *)take((size_t)emax * 4 + 4);
+    a.buckets = (uint32_t *)take((size_t)a.K * JACB);
+    a.edges = (uint32_t *)take((size_t)a.max_chunks * 2 * JACB);
+    a.edge_bucket = (uint32_t *)take((size_t)a.max_chunks * 2 * 4);
+    {
+        const size_t n1 = (a.max_chunks + FOLD_GS - 1) / FOLD_GS, n2 = (n1 + FOLD_GS - 1) / FOLD_GS;
+        a.fold_pts[0] = (uint32_t *)take(n1 * 2 * JACB);
+        a.fold_key[0] = (uint32_t *)take(n1 * 2 * 4);
+        a.fold_pts[1] = (uint32_t *)take(n2 * 2 * JACB);
+        a.fold_key[1] = (uint32_t *)take(n2 * 2 * 4);
+    }
+    a.segsum = (uint32_t *)take((size_t)a.W * a.nseg * JACB);
+    const size_t lvl = (size_t)a.W * ((a.nseg + 31) / 32) * JACB;
+    a.tmp_a = (uint32_t *)take(lvl);
+    a.tmp_b = (uint32_t *)take(lvl);
+    a.winsum = (uint32_t *)take((size_t)a.W * JACB);
+    a.result = (uint32_t *)take(JACB);
+    p.bytes = off;
+    return p;
+}
+
+template <class K>
+int set_smem(b200msm_ctx *ctx, K kernel, size_t bytes) {
+    CU(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return B200MSM_OK;
+}
+
+int grow_arena(b200msm_ctx *ctx, Lane &ln, size_t bytes) {
+    if (bytes <= ln.arena_bytes) return B200MSM_OK;
+    CU(cudaStreamSynchronize(ln.stream));
+    if (ln.arena) CU(cudaFree(ln.arena));
+    ln.arena = nullptr;
+    ln.arena_bytes = 0;
+    const size_t want = bytes + bytes / 8;
+    CU(cudaMalloc(&ln.arena, want));
+    ln.arena_bytes = want;
+    return B200MSM_OK;
+}
+
+// Enqueue one MSM on lane `li`.  scalars: host or device pointer (Montgomery Fr).
+template <class G>
+int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, const uint64_t *scalars, size_t n,
+                uint64_t *out_xyz) {
+    typedef typename G::F F;
+    typedef AccCfg<G> AC;
+    typedef TailCfg<G> TC;
+    constexpr int DEG = F::DEG;
+    constexpr size_t AFFW = 2 * DEG * NLIMB, JACW = 3 * DEG * NLIMB;
+    Lane &ln = ctx->lanes[li];
+    cudaStream_t st = ln.stream;
+    ln.out_words = JACW / 2;
+    ln.user_out = out_xyz;
+
+    if (n == 0) {
+        // empty sum: infinity, reported as (1, 1, 0) in Montgomery form like curves.cu:104-114
+        memset(ln.h_result, 0, JACW * 4);
+        for (int i = 0; i < NLIMB; ++i) {
+            ln.h_result[i] = F::M::R1(i);
+            ln.h_result[DEG * NLIMB + i] = F::M::R1(i);
+        }
+        ln.pending = true;
+        ln.timed = false;
+        memset(ln.ms, 0, sizeof ln.ms);
+        memset(ln.info, 0, sizeof ln.info);
+        return B200MSM_OK;
+    }
+
+    // window tables are used when they exist and the caller did not force a different window width
+    TabCfg cfg;
+    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) cfg = {bs.c_tab, digits_for(bs.c_tab), bs.NT, bs.G};
+    else cfg = choose_cfg(n, DEG, ctx->c_override, 0, false);
+    const int c = cfg.c;
+    Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
+    int rc = grow_arena(ctx, ln, probe.bytes);
+    if (rc) return rc;
+    Plan p = make_plan<G>(ctx, n, cfg, ln.arena);
+    MsmArgs &a = p.a;
+    a.bases = bs.pts + offset * AFFW;
+    a.base_inf = bs.inf + offset;
+    a.tab_stride = (uint32_t)bs.n;
+
+    if ((rc = set_smem(ctx, k_accumulate<G>, AC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_fold_edges<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_bucket_reduce<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_sum<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_horner<G>, TC::TS::SMEM))) return rc;
+
+    uint64_t launches = 0;
+    CU(cudaEventRecord(ln.ev[0], st));
+    CU(cudaMemcpyAsync(a.scalars, scalars, n * NLIMB * 4, cudaMemcpyDefault, st));
+    CU(cudaEventRecord(ln.ev[1], st));
+
+    const unsigned nb128 = (unsigned)((n + 127) / 128), nb256 = (unsigned)((n + 255) / 256);
+    k_from_mont<typename G::Fr><<<nb128, 128, 0, st>>>(a.scalars, a.n);
+    CU(cudaMemsetAsync(a.count, 0, (size_t)a.K * 4, st));
+    k_count<<<nb256, 256, 0, st>>>(a);
+    k_scan_local<<<p.nscan, SCAN_T, 0, st>>>(a.count, a.offs, p.bsum, a.K);
+    k_scan_bsum<<<1, SCAN_T, 0, st>>>(p.bsum, p.nscan, a.offs + a.K);
+    k_scan_add<<<p.nscan, SCAN_T, 0, st>>>(a.offs, a.cursor, p.bsum, a.K);
+    k_scatter<<<nb256, 256, 0, st>>>(a);
+    launches += 6;
+    CU(cudaEventRecord(ln.ev[2], st));
+
+    CU(cudaMemsetAsync(a.group_counter, 0, 4, st));
+    CU(cudaMemsetAsync(a.edge_bucket, 0xff, (size_t)a.max_chunks * 2 * 4, st));
+    k_accumulate<G><<<ctx->sm_count * AC::MINB, AC::TS::THREADS, AC::TS::SMEM, st>>>(a);
+    launches += 1;
+    CU(cudaEventRecord(ln.ev[3], st));
+
+    const unsigned tail_lanes = TC::TPB * 32;
+    {
+        const uint32_t *in_pts = a.edges, *in_key = a.edge_bucket;
+        uint32_t n_in = a.max_chunks;
+        unsigned long long span = a.L;
+        int flip = 0;
+        do {
+            const uint32_t n_out = (n_in + FOLD_GS - 1) / FOLD_GS;
+            span *= FOLD_GS;
+            k_fold_edges<G><<<(n_out + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(
+                a, in_pts, in_key, n_in, a.fold_pts[flip], a.fold_key[flip], n_out, span);
+            ++launches;
+            in_pts = a.fold_pts[flip];
+            in_key = a.fold_key[flip];
+            n_in = n_out;
+            flip ^= 1;
+        } while (n_in > 1);
+    }
+    k_bucket_reduce<G><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
+    launches += 1;
+    {
+        const uint32_t *in = a.segsum;
+        uint32_t nin = a.nseg;
+        uint32_t *bufs[2] = {a.tmp_a, a.tmp_b};
+        int flip = 0;
+        while (nin > 1) {
+            const uint32_t nout = (nin + 31) / 32;
+            uint32_t *out = nout == 1 ? a.winsum : bufs[flip];
+            k_sum<G><<<((unsigned)a.W * nout + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(
+                in, out, (uint32_t)a.W, nin, 32u);
+            ++launches;
+            in = out;
+            nin = nout;
+            flip ^= 1;
+        }
+        if (in != a.winsum) a.winsum = const_cast<uint32_t *>(in);  // nseg == 1: segment sums are the window sums
+    }
+    k_horner<G><<<1, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
+    ++launches;
+    CU(cudaEventRecord(ln.ev[4], st));
+    CU(cudaMemcpyAsync(ln.h_result, a.result, JACW * 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaEventRecord(ln.ev[5], st));
+    CU(cudaGetLastError());
+
+    ln.pending = true;
+    ln.timed = true;
+    ln.info[0] = (uint64_t)c;
+    ln.info[1] = (uint64_t)a.Wd;
+    ln.info[2] = (uint64_t)n * a.Wd;
+    ln.info[3] = 1;
+    ln.info[4] = launches;
+    ln.info[5] = (uint64_t)a.W;
+    ln.info[6] = (uint64_t)cfg.NT;
+    ln.info[7] = 0;
+    return B200MSM_OK;
+}
+
+// ---- self-test kernels: the field / point layer exposed elementwise (tests only) --------------
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_test_field(int op, uint32_t n, const uint32_t *x, const uint32_t *y, uint32_t *out) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    constexpr int EW = F::DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + (threadIdx.x & 31);
+    const bool v = id < n;
+    g2s(T, 0, x + (size_t)id * EW, v);
+    g2s(T, 1, (y ? y : x) + (size_t)id * EW, v);
+    T.set_zero(0, !v);
+    T.set_zero(1, !v);
+    T.sync();
+    switch (op) {
+        case 0: T.mul(2, 0, 1); break;
+        case 1: T.add(2, 0, 1); break;
+        case 2: T.sub(2, 0, 1); break;
+        case 3: T.sqr(2, 0); break;
+        case 5: T.neg_if(2, 0, true); break;
+        case 6: T.mul_by_a(2, 0); break;
+        case 7: T.mul(0, 0, 1); T.copy(2, 0); break;
+        default: T.dbl(2, 0); break;
+    }
+    T.sync();
+    s2g(T, out + (size_t)id * EW, 2, v);
+}
+
+// op 0: acc (Jacobian) += q (affine, optional negation flag bit0; bit1: acc is infinity); op 1: full add; op 2: dbl
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_test_point(int op, uint32_t n, const uint32_t *acc, const uint32_t *q, const uint32_t *flags, uint32_t *out) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    constexpr int EW = F::DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + (threadIdx.x & 31);
+    const bool v = id < n;
+    const PtSlots s = {0, 1, 2, 6, 7, 8, 9, 10, 11};
+    load_jac(T, s.X1, s.Y1, s.Z1, acc + (size_t)id * 3 * EW, v);
+    T.set_zero(s.X1, !v); T.set_zero(s.Y1, !v); T.set_zero(s.Z1, !v);
+    const uint32_t fl = (v && flags) ? flags[id] : 0u;
+    if (op == 0) {
+        g2s(T, s.X2, q + (size_t)id * 2 * EW, v);
+        g2s(T, s.Y2, q + (size_t)id * 2 * EW + EW, v);
+        T.set_zero(s.X2, !v); T.set_zero(s.Y2, !v);
+        bool acc_inf = (fl & 2u) != 0;
+        Ec<F>::madd(T, s, (fl & 1u) != 0, v, acc_inf);
+        T.set_zero(s.Z1, acc_inf);
+    } else if (op == 1) {
+        load_jac(T, s.X2, s.Y2, s.Z2, q + (size_t)id * 3 * EW, v);
+        T.set_zero(s.X2, !v); T.set_zero(s.Y2, !v); T.set_zero(s.Z2, !v);
+        Ec<F>::add(T, s, v);
+    } else {
+        Ec<F>::dbl(T, s, v);
+    }
+    T.sync();
+    store_jac(T, out + (size_t)id * 3 * EW, s.X1, s.Y1, s.Z1, v);
+}
+
+template <class G>
+int run_test(b200msm_ctx *ctx, bool point, int op, size_t n, const uint64_t *a, const uint64_t *b, const uint32_t *flags, uint64_t *out) {
+    typedef TailCfg<G> TC;
+    constexpr size_t EB = G::F::DEG * NLIMB * 4;
+    const size_t ab = point ? 3 * EB : EB, bb = point ? (op == 0 ? 2 * EB : 3 * EB) : EB, ob = ab;
+    uint32_t *da = nullptr, *db = nullptr, *dout = nullptr, *dfl = nullptr;
+    CU(cudaMalloc(&da, n * ab));
+    CU(cudaMalloc(&dout, n * ob));
+    CU(cudaMemcpy(da, a, n * ab, cudaMemcpyHostToDevice));
+    if (b) { CU(cudaMalloc(&db, n * bb)); CU(cudaMemcpy(db, b, n * bb, cudaMemcpyHostToDevice)); }
+    if (flags) { CU(cudaMalloc(&dfl, n * 4)); CU(cudaMemcpy(dfl, flags, n * 4, cudaMemcpyHostToDevice)); }
+    const unsigned lanes = TC::TPB * 32, grid = (unsigned)((n + lanes - 1) / lanes);
+    if (point) {
+        CU(cudaFuncSetAttribute(k_test_point<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+        k_test_point<G><<<grid, TC::TS::THREADS, TC::TS::SMEM>>>(op, (uint32_t)n, da, db, dfl, dout);
+    } else {
+        CU(cudaFuncSetAttribute(k_test_field<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+        k_test_field<G><<<grid, TC::TS::THREADS, TC::TS::SMEM>>>(op, (uint32_t)n, da, db, dout);
+    }
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, dout, n * ob, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dfl);
+    return B200MSM_OK;
+}
+
+// sum of n Jacobian partial results (one per GPU shard) on the device -> one Jacobian point
+template <class G>
+int run_fold(b200msm_ctx *ctx, const uint64_t *xyz, size_t n, uint64_t *out) {
+    typedef TailCfg<G> TC;
+    constexpr size_t JACW = 3 * G::F::DEG * NLIMB, JACB = JACW * 4;
+    const size_t lvl = (n + 31) / 32 + 1;
+    uint32_t *din = nullptr, *buf[2] = {nullptr, nullptr}, *dres = nullptr;
+    CU(cudaMalloc(&din, (n ? n : 1) * JACB));
+    CU(cudaMalloc(&buf[0], lvl * JACB));
+    CU(cudaMalloc(&buf[1], lvl * JACB));
+    CU(cudaMalloc(&dres, JACB));
+    CU(cudaMemcpy(din, xyz, n * JACB, cudaMemcpyDefault));
+    CU(cudaFuncSetAttribute(k_sum<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    CU(cudaFuncSetAttribute(k_horner<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    const unsigned tail_lanes = TC::TPB * 32;
+    const uint32_t *in = din;
+    uint32_t nin = (uint32_t)n;
+    int flip = 0;
+    do {  // at least one pass so that the input is never aliased
+        const uint32_t nout = (nin + 31) / 32;
+        k_sum<G><<<(nout + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM>>>(in, buf[flip], 1u, nin, 32u);
+        in = buf[flip];
+        nin = nout;
+        flip ^= 1;
+    } while (nin > 1);
+    MsmArgs a;
+    memset(&a, 0, sizeof a);
+    a.W = 1;
+    a.c = 1;
+    a.winsum = const_cast<uint32_t *>(in);
+    a.result = dres;
+    k_horner<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>(a);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, dres, JACB, cudaMemcpyDeviceToHost));
+    cudaFree(din); cudaFree(buf[0]); cudaFree(buf[1]); cudaFree(dres);
+    return B200MSM_OK;
+}
+
+// ---- affine normalisation / synthetic bases ---------------------------------------------------
+// exponent q^DEG - 2 of the Fermat inversion in Fq^DEG, little-endian 32-bit words
+template <class G>
+std::vector<uint32_t> fermat_exponent() {
+    constexpr int DEG = G::F::DEG;
+    std::vector<uint32_t> q(NLIMB), acc(1, 1u);
+    for (int i = 0; i < NLIMB; ++i) q[i] = G::F::M::P(i);
+    for (int d = 0; d < DEG; ++d) {
+        std::vector<uint32_t> r(acc.size() + NLIMB, 0u);
+        for (size_t i = 0; i < acc.size(); ++i) {
+            uint64_t carry = 0;
+            for (int j = 0; j < NLIMB; ++j) {
+                uint64_t t = (uint64_t)acc[i] * q[j] + r[i + j] + carry;
+                r[i + j] = (uint32_t)t;
+                carry = t >> 32;
+            }
+            r[i + NLIMB] = (uint32_t)carry;
+        }
+        acc.swap(r);
+    }
+    uint64_t borrow = 2;  // acc -= 2 (q is odd and > 2, so no underflow)
+    for (size_t i = 0; i < acc.size() && borrow; ++i) {
+        uint64_t t = (uint64_t)acc[i] - borrow;
+        acc[i] = (uint32_t)t;
+        borrow = (t >> 63) & 1u;
+    }
+    return acc;
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
+template <class G>
+int upload_exponent(b200msm_ctx *ctx, DevBuf &d, int &bits) {
+    std::vector<uint32_t> e = fermat_exponent<G>();
+    bits = G::F::DEG * MNT753_NUM_BITS;
+    CU(cudaMalloc(&d.p, e.size() * 4));
+    CU(cudaMemcpy(d.p, e.data(), e.size() * 4, cudaMemcpyHostToDevice));
+    return B200MSM_OK;
+}
+
+template <class G>
+int run_to_affine(b200msm_ctx *ctx, size_t n, const uint64_t *xyz, uint64_t *out) {
+    typedef TailCfg<G> TC;
+    constexpr size_t EB = G::F::DEG * NLIMB * 4;
+    DevBuf e, in, o;
+    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
+    if (rc) return rc;
+    CU(cudaMalloc(&in.p, n * 3 * EB));
+    CU(cudaMalloc(&o.p, n * 2 * EB));
+    CU(cudaMemcpy(in.p, xyz, n * 3 * EB, cudaMemcpyDefault));
+    CU(cudaFuncSetAttribute(k_to_affine<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    const unsigned lanes = TC::TPB * 32;
+    k_to_affine<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, (const uint32_t *)in.p, (uint32_t *)o.p,
+                                                                                         (const uint32_t *)e.p, bits);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, o.p, n * 2 * EB, cudaMemcpyDefault));
+    return B200MSM_OK;
+}
+
+template <class G>
+const uint32_t *generator_words() {
+    static const uint32_t c0g1[] = MNT753_GEN_C0_G1_U32, c0g2[] = MNT753_GEN_C0_G2_U32, c1g1[] = MNT753_GEN_C1_G1_U32,
+                          c1g2[] = MNT753_GEN_C1_G2_U32;
+    return G::CURVE == 0 ? (G::GROUP == 1 ? c0g1 : c0g2) : (G::GROUP == 1 ? c1g1 : c1g2);
+}
+
+// Build window tables 1 .. NT-1 of a base set whose table 0 (the points) is already in place:
+// table t = 2^(c*G) * table t-1, each normalised back to affine with one inversion per 32-point run.
+template <class G>
+int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
+    typedef TailCfg<G> TC;
+    constexpr size_t EB = G::F::DEG * NLIMB * 4;
+    constexpr uint32_t B = 32;
+    if (bs.NT <= 1 || bs.n == 0) return B200MSM_OK;
+    DevBuf e, jac, pre;
+    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
+    if (rc) return rc;
+    const size_t n = bs.n;
+    CU(cudaMalloc(&jac.p, n * 3 * EB));
+    CU(cudaMalloc(&pre.p, n * EB));
+    CU(cudaFuncSetAttribute(k_dbl_many<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    CU(cudaFuncSetAttribute(k_batch_normalise<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, 0));
+    const unsigned lanes = TC::TPB * 32;
+    const size_t runs = (n + B - 1) / B;
+    const size_t tabw = n * 2 * (EB / 4);
+    for (int t = 1; t < bs.NT; ++t) {
+        k_dbl_many<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, bs.c_tab * bs.G, bs.pts + (t - 1) * tabw,
+                                                                                            (uint32_t *)jac.p);
+        k_batch_normalise<G><<<(unsigned)((runs + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>(
+            (uint32_t)n, B, (const uint32_t *)jac.p, (uint32_t *)pre.p, bs.pts + t * tabw, (const uint32_t *)e.p, bits);
+    }
+    CU(cudaEventRecord(e1, 0));
+    CU(cudaGetLastError());
+    CU(cudaEventSynchronize(e1));
+    CU(cudaEventElapsedTime(&bs.build_ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return B200MSM_OK;
+}
+
+// bases[i] = k_p0 * G + i * (k_q * G), written straight into a new resident base set
+template <class G>
+int run_synthetic(b200msm_ctx *ctx, size_t n, const uint64_t *k_p0, const uint64_t *k_q, BaseSet &bs) {
+    typedef TailCfg<G> TC;
+    constexpr size_t EB = G::F::DEG * NLIMB * 4;
+    constexpr uint32_t B = 64;
+    DevBuf e, gen, ks, pj, pa, jac, pre;
+    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
+    if (rc) return rc;
+    CU(cudaMalloc(&gen.p, 2 * EB));
+    CU(cudaMalloc(&ks.p, 2 * NLIMB * 4));
+    CU(cudaMalloc(&pj.p, 2 * 3 * EB));
+    CU(cudaMalloc(&pa.p, 2 * 2 * EB));
+    CU(cudaMalloc(&jac.p, n * 3 * EB));
+    CU(cudaMalloc(&pre.p, n * EB));
+    CU(cudaMemcpy(gen.p, generator_words<G>(), 2 * EB, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(ks.p, k_p0, NLIMB * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy((uint32_t *)ks.p + NLIMB, k_q, NLIMB * 4, cudaMemcpyHostToDevice));
+    CU(cudaFuncSetAttribute(k_scalar_mul<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    CU(cudaFuncSetAttribute(k_to_affine<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    CU(cudaFuncSetAttribute(k_synth_bases<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    for (int i = 0; i < 2; ++i)
+        k_scalar_mul<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>((const uint32_t *)gen.p, (const uint32_t *)ks.p + i * NLIMB,
+                                                             (uint32_t *)pj.p + i * 3 * (EB / 4));
+    k_to_affine<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>(2u, (const uint32_t *)pj.p, (uint32_t *)pa.p, (const uint32_t *)e.p, bits);
+    const unsigned lanes = TC::TPB * 32;
+    const size_t runs = (n + B - 1) / B;
+    k_synth_bases<G><<<(unsigned)((runs + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>(
+        (uint32_t)n, B, (const uint32_t *)pa.p, (const uint32_t *)pa.p + 2 * (EB / 4), bs.pts, (uint32_t *)jac.p, (uint32_t *)pre.p,
+        (const uint32_t *)e.p, bits);
+    constexpr int DEG = G::F::DEG;
+    k_flag_inf<DEG><<<(unsigned)((n + 255) / 256), 256>>>(bs.pts, (uint32_t)n, bs.inf);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    return B200MSM_OK;
+}
+
+}  // namespace
+
+
+template <class G>
+constexpr GroupOps make_group_ops() {
+    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>};
+}

@@ -1,0 +1,139 @@
+// Host-side state shared by the translation units of libb200msm.so (msm.cu holds the C ABI, inst_*.cu
+// the per-group kernels).  One context per (curve, GPU); four internal streams ("lanes") so that the
+// A, B1, B2 and L multiexps of one proof can be in flight together, as the reference does with one
+// stream per MSM (cuda_prover_piecewise.cu:162-167).
+#pragma once
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200_msm.h"
+#include "msm_kernels.cuh"
+#include "util_kernels.cuh"
+
+using namespace mnt753;
+
+constexpr int NLANES = 4;
+constexpr int NEVENTS = 7;
+
+// A resident base set.  Besides the points themselves (table 0) it may hold NT - 1 further
+// "window tables": table t = 2^(c*G*t) * P_i, affine, row t*n + i of `pts`.  Signed digit w of a
+// scalar then adds table (w / G) into bucket set (w % G), so an MSM needs only G = ceil(Wd / NT)
+// bucket sets, G running-sum reductions and (G - 1) * c doublings in the window combine, instead of
+// Wd = ceil(754 / c) of each.  With NT = Wd there is a single bucket set and no combine at all.
+// This is the engine's use of HBM capacity (180 GB): the reference spent 25 GB of *disk* on its
+// 31x multiples table (main.cpp:311-339); these tables are built on the device at upload time.
+struct BaseSet {
+    bool used = false;
+    int group = 0;
+    size_t n = 0;
+    uint32_t *pts = nullptr;
+    uint8_t *inf = nullptr;
+    int c_tab = 0;  // window bits the tables were built for (0: no tables, any c allowed)
+    int NT = 1;     // number of tables
+    int G = 0;      // bucket sets when the tables are used
+    float build_ms = 0.f;
+};
+
+struct Lane {
+    cudaStream_t stream = nullptr;      // stream MSMs are enqueued on
+    cudaStream_t own_stream = nullptr;  // the lane's internal stream (stream == own_stream unless overridden)
+    cudaEvent_t ev[NEVENTS] = {};
+    char *arena = nullptr;
+    size_t arena_bytes = 0;
+    uint32_t *h_result = nullptr;  // pinned staging for the Jacobian result
+    uint64_t *user_out = nullptr;
+    size_t out_words = 0;
+    bool pending = false;
+    bool timed = false;
+    float ms[6] = {};
+    uint64_t info[8] = {};
+};
+
+struct b200msm_ctx {
+    int curve = 0;
+    int device = 0;
+    int sm_count = 0;
+    int c_override = 0;
+    size_t table_budget = size_t(32) << 30;  // bytes of window tables per base set (0: never build tables)
+    std::vector<BaseSet> sets;
+    Lane lanes[NLANES];
+    std::string err = "";
+};
+
+namespace {
+
+int fail(b200msm_ctx *ctx, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? B200MSM_ERR_OOM : B200MSM_ERR_CUDA, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+inline int degree_of(int curve, int group) { return group == B200MSM_G1 ? 1 : (curve == B200MSM_MNT4753 ? 2 : 3); }
+
+// ---- window-size / table choice ---------------------------------------------------------------
+// Time model in nanoseconds, calibrated on B200 (profiles/): one mixed addition per point and digit in
+// k_accumulate, one bucket in the running-sum reduction, and the serial window combine (c doublings per
+// bucket set after the first; a lone lane runs them at the latency of one Fq product each).
+struct TabCfg { int c, Wd, NT, G; };
+inline int digits_for(int c) { return (MNT753_NUM_BITS + 1 + c - 1) / c; }
+
+TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bool tables) {
+    const double k = deg == 1 ? 1.0 : (deg == 2 ? 3.0 : 6.0);
+    const size_t affb = (size_t)2 * deg * NLIMB * 4;
+    TabCfg best = {2, digits_for(2), 1, digits_for(2)};
+    double best_cost = 1e300;
+    for (int c = (c_fixed ? c_fixed : 2); c <= (c_fixed ? c_fixed : 22); ++c) {
+        const int Wd = digits_for(c);
+        size_t nt = 1;
+        if (tables && n >= 256 && budget_bytes) {
+            nt = budget_bytes / (n * affb);
+            const size_t idx_cap = ((size_t(1) << 31) - 1) / n;
+            if (nt > idx_cap) nt = idx_cap;
+            if (nt > (size_t)Wd) nt = Wd;
+            if (nt < 1) nt = 1;
+        }
+        const int G = (Wd + (int)nt - 1) / (int)nt;
+        const int NT = (Wd + G - 1) / G;
+        const double NB = double(1u << (c - 1));
+        const double cost = double(Wd) * double(n) * 1.63 * k + double(G) * NB * 8.6 * k + double(G - 1) * c * 40000.0 * deg +
+                            double(G) * 60000.0 * deg;
+        if (cost < best_cost) { best_cost = cost; best = {c, Wd, NT, G}; }
+    }
+    return best;
+}
+
+struct Plan {
+    MsmArgs a;
+    size_t bytes;
+    uint32_t *bsum;
+    uint32_t nscan;
+};
+
+size_t align_up(size_t x, size_t al) { return (x + al - 1) / al * al; }
+
+}  // namespace
+
+// per-group entry points (inst_*.cu)
+struct GroupOps {
+    int (*enqueue)(b200msm_ctx *, int, const BaseSet &, size_t, const uint64_t *, size_t, uint64_t *);
+    int (*selftest)(b200msm_ctx *, bool, int, size_t, const uint64_t *, const uint64_t *, const uint32_t *, uint64_t *);
+    int (*fold)(b200msm_ctx *, const uint64_t *, size_t, uint64_t *);
+    int (*to_affine)(b200msm_ctx *, size_t, const uint64_t *, uint64_t *);
+    int (*synthetic)(b200msm_ctx *, size_t, const uint64_t *, const uint64_t *, BaseSet &);
+    int (*build_tables)(b200msm_ctx *, BaseSet &);
+};

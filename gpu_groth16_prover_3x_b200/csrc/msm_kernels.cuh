@@ -29,21 +29,23 @@ struct MsmArgs {
     // problem
     uint32_t n;        // number of points
     int c;             // window width in bits
-    int W;             // number of windows
-    uint32_t NB;       // buckets per window = 2^(c-1)
+    int Wd;            // number of signed digits (windows) per scalar = ceil(754 / c)
+    int W;             // number of bucket sets = ceil(Wd / NT): digit w lands in set w % W, using table w / W
+    uint32_t tab_stride;  // points per precomputed table (table t holds 2^(c*W*t) * P_i), see BaseSet
+    uint32_t NB;       // buckets per set = 2^(c-1)
     uint32_t K;        // W * NB
     uint32_t L;        // sorted-list entries per lane chunk
     uint32_t max_chunks;
     uint32_t m;        // bucket-reduce segment length (power of two)
     uint32_t nseg;     // NB / m
     // buffers
-    const uint32_t *bases;      // affine AoS, 2*DEG*24 words per point
+    const uint32_t *bases;      // affine AoS, 2*DEG*24 words per point; row t * tab_stride + i = 2^(c*W*t) * P_i
     const uint8_t *base_inf;    // 1 if base is infinity
     uint32_t *scalars;          // n * 24 words; Montgomery in, plain integer after k_from_mont
     uint32_t *count;            // K
     uint32_t *offs;             // K + 1
     uint32_t *cursor;           // K
-    uint32_t *entries;          // n * W : point index | sign << 31
+    uint32_t *entries;          // n * Wd : table row | sign << 31
     uint32_t *buckets;          // K Jacobian points (3*DEG*24 words each)
     uint32_t *edges;            // max_chunks * 2 Jacobian points
     uint32_t *edge_bucket;      // max_chunks * 2, preset to EDGE_NONE by the host
@@ -167,34 +169,34 @@ __device__ __forceinline__ void for_each_digit(const uint32_t *k, int c, int W, 
     }
 }
 
-__global__ void k_count(MsmArgs a) {
+static __global__ void k_count(MsmArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n || a.base_inf[i]) return;
     uint32_t k[NLIMB];
     const uint4 *p = reinterpret_cast<const uint4 *>(a.scalars + (size_t)i * NLIMB);
     for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w; }
-    for_each_digit(k, a.c, a.W, [&](int w, int d) {
+    for_each_digit(k, a.c, a.Wd, [&](int w, int d) {
         uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
-        atomicAdd(&a.count[(uint32_t)w * a.NB + b], 1u);
+        atomicAdd(&a.count[(uint32_t)(w % a.W) * a.NB + b], 1u);
     });
 }
 
-__global__ void k_scatter(MsmArgs a) {
+static __global__ void k_scatter(MsmArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n || a.base_inf[i]) return;
     uint32_t k[NLIMB];
     const uint4 *p = reinterpret_cast<const uint4 *>(a.scalars + (size_t)i * NLIMB);
     for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w; }
-    for_each_digit(k, a.c, a.W, [&](int w, int d) {
+    for_each_digit(k, a.c, a.Wd, [&](int w, int d) {
         uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
-        uint32_t pos = atomicAdd(&a.cursor[(uint32_t)w * a.NB + b], 1u);
-        a.entries[pos] = i | (d < 0 ? 0x80000000u : 0u);
+        uint32_t pos = atomicAdd(&a.cursor[(uint32_t)(w % a.W) * a.NB + b], 1u);
+        a.entries[pos] = ((uint32_t)(w / a.W) * a.tab_stride + i) | (d < 0 ? 0x80000000u : 0u);
     });
 }
 
 // ---- exclusive scan of count[0..K) -> offs[0..K], offs[K] = total -----------------------------
 constexpr int SCAN_T = 256, SCAN_E = 4, SCAN_B = SCAN_T * SCAN_E;
-__global__ void __launch_bounds__(SCAN_T) k_scan_local(const uint32_t *in, uint32_t *out, uint32_t *bsum, uint32_t K) {
+static __global__ void __launch_bounds__(SCAN_T) k_scan_local(const uint32_t *in, uint32_t *out, uint32_t *bsum, uint32_t K) {
     __shared__ uint32_t sh[SCAN_T];
     uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
     uint32_t v[SCAN_E], s = 0;
@@ -211,7 +213,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_local(const uint32_t *in, uint3
     for (int e = 0; e < SCAN_E; ++e) { if (base + e < K) out[base + e] = excl; excl += v[e]; }
     if (threadIdx.x == SCAN_T - 1) bsum[blockIdx.x] = sh[SCAN_T - 1];
 }
-__global__ void __launch_bounds__(SCAN_T) k_scan_bsum(uint32_t *bsum, uint32_t nb, uint32_t *total) {
+static __global__ void __launch_bounds__(SCAN_T) k_scan_bsum(uint32_t *bsum, uint32_t nb, uint32_t *total) {
     __shared__ uint32_t sh[SCAN_T];
     __shared__ uint32_t carry;
     if (threadIdx.x == 0) carry = 0;
@@ -234,7 +236,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_bsum(uint32_t *bsum, uint32_t n
     }
     if (threadIdx.x == 0) *total = carry;
 }
-__global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t *out, uint32_t *cursor, const uint32_t *bsum, uint32_t K) {
+static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t *out, uint32_t *cursor, const uint32_t *bsum, uint32_t K) {
     uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
     uint32_t add = bsum[blockIdx.x];
     for (int e = 0; e < SCAN_E; ++e)

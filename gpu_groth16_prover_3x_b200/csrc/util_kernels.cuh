@@ -36,6 +36,42 @@ __device__ void small_scalar_mul(const Team<F> &T, const PtSlots &s, uint32_t k,
     }
 }
 
+// Second half of Montgomery's simultaneous inversion for one lane's run [start, start + B) of Jacobian
+// points: on entry slot PRE holds the product of the run's (non-zero-substituted) Z coordinates and
+// prefix[idx] the inclusive prefix products; writes affine(jac[idx]) to out (infinity -> all zero).
+template <class F>
+__device__ void normalise_run(const Team<F> &T, uint32_t start, uint32_t B, uint32_t n, bool valid, const uint32_t *jac,
+                              const uint32_t *prefix, uint32_t *out, const uint32_t *e, int ebits) {
+    typedef UtilSlots U;
+    constexpr int EW = F::DEG * NLIMB, AFFW = 2 * EW, JACW = 3 * EW;
+    team_pow(T, U::INV, U::PRE, e, ebits);
+    for (int j = (int)B - 1; j >= 0; --j) {
+        const uint32_t idx = start + (uint32_t)j;
+        const bool act = valid && idx < n;
+        if (!team_any(act)) continue;
+        const uint32_t *pj = jac + (size_t)idx * JACW;
+        g2s(T, U::X1, pj, act);
+        g2s(T, U::Y1, pj + EW, act);
+        g2s(T, U::TMP, pj + 2 * EW, act);
+        if (j > 0) g2s(T, U::Z2, prefix + (size_t)(idx - 1) * EW, act);
+        T.sync();
+        if (j == 0) T.set_one(U::Z2);
+        const bool inf = T.is_zero(U::TMP);
+        T.set_one(U::TMP, inf);
+        T.mul(U::T0, U::INV, U::Z2);           // 1 / Z_j
+        T.mul(U::INV, U::INV, U::TMP, act);    // inverse of the shorter prefix
+        T.sqr(U::T1, U::T0);
+        T.mul(U::X1, U::X1, U::T1);
+        T.mul(U::T1, U::T1, U::T0);
+        T.mul(U::Y1, U::Y1, U::T1);
+        T.set_zero(U::X1, inf);
+        T.set_zero(U::Y1, inf);
+        T.sync();
+        s2g(T, out + (size_t)idx * AFFW, U::X1, act);
+        s2g(T, out + (size_t)idx * AFFW + EW, U::Y1, act);
+    }
+}
+
 // out[i] = affine(P0 + i*Q), i < n.  One lane per run of B consecutive indices.
 template <class G>
 __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_synth_bases(uint32_t n, uint32_t B, const uint32_t *p0, const uint32_t *q,
@@ -81,32 +117,65 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_synth_bases(uint32_
         s2g(T, prefix + (size_t)idx * EW, U::PRE, act);
         Ec<F>::madd(T, s, false, act, acc_inf);
     }
-    team_pow(T, U::INV, U::PRE, e, ebits);
-    for (int j = (int)B - 1; j >= 0; --j) {
-        const uint32_t idx = start + (uint32_t)j;
+    normalise_run<F>(T, start, B, n, valid, jac, prefix, out, e, ebits);
+}
+
+// ---- precomputed window tables -------------------------------------------------------------------
+// jac[i] = 2^s * in[i] for n affine points (infinity, encoded y == 0, stays infinity: Z = 2*Y*Z = 0).
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_dbl_many(uint32_t n, int s_dbl, const uint32_t *in, uint32_t *jac) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    typedef UtilSlots U;
+    constexpr int EW = F::DEG * NLIMB;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const PtSlots s = {U::X1, U::Y1, U::Z1, U::X2, U::Y2, U::Z2, U::T0, U::T1, U::T2};
+    const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + (threadIdx.x & 31);
+    const bool act = id < n;
+    g2s(T, U::X1, in + (size_t)id * 2 * EW, act);
+    g2s(T, U::Y1, in + (size_t)id * 2 * EW + EW, act);
+    T.set_zero(U::X1, !act); T.set_zero(U::Y1, !act);
+    T.set_one(U::Z1);
+    T.sync();
+    for (int i = 0; i < s_dbl; ++i) Ec<F>::dbl(T, s, true);
+    T.sync();
+    store_jac(T, jac + (size_t)id * 3 * EW, U::X1, U::Y1, U::Z1, act);
+}
+
+// out[i] = affine(jac[i]), i < n: one lane per run of B consecutive points, one Fermat inversion per lane.
+template <class G>
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_batch_normalise(uint32_t n, uint32_t B, const uint32_t *jac, uint32_t *prefix,
+                                                                             uint32_t *out, const uint32_t *e, int ebits) {
+    typedef typename G::F F;
+    typedef TailCfg<G> C;
+    typedef UtilSlots U;
+    constexpr int EW = F::DEG * NLIMB, JACW = 3 * EW;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + (threadIdx.x & 31);
+    const uint64_t start64 = (uint64_t)id * B;
+    const bool valid = start64 < n;
+    const uint32_t start = valid ? (uint32_t)start64 : 0u;
+    T.set_one(U::PRE);
+    for (uint32_t j = 0; j < B; ++j) {
+        const uint32_t idx = start + j;
         const bool act = valid && idx < n;
-        if (!team_any(act)) continue;
-        const uint32_t *pj = jac + (size_t)idx * JACW;
-        g2s(T, U::X1, pj, act);
-        g2s(T, U::Y1, pj + EW, act);
-        g2s(T, U::TMP, pj + 2 * EW, act);
-        if (j > 0) g2s(T, U::Z2, prefix + (size_t)(idx - 1) * EW, act);
+        if (!team_any(act)) break;
+        g2s(T, U::TMP, jac + (size_t)idx * JACW + 2 * EW, act);
         T.sync();
-        if (j == 0) T.set_one(U::Z2);
         const bool inf = T.is_zero(U::TMP);
-        T.set_one(U::TMP, inf);
-        T.mul(U::T0, U::INV, U::Z2);           // 1 / Z_j
-        T.mul(U::INV, U::INV, U::TMP, act);    // inverse of the shorter prefix
-        T.sqr(U::T1, U::T0);
-        T.mul(U::X1, U::X1, U::T1);
-        T.mul(U::T1, U::T1, U::T0);
-        T.mul(U::Y1, U::Y1, U::T1);
-        T.set_zero(U::X1, inf);
-        T.set_zero(U::Y1, inf);
+        T.set_one(U::TMP, inf || !act);
+        T.mul(U::PRE, U::PRE, U::TMP, act);
         T.sync();
-        s2g(T, out + (size_t)idx * AFFW, U::X1, act);
-        s2g(T, out + (size_t)idx * AFFW + EW, U::Y1, act);
+        s2g(T, prefix + (size_t)idx * EW, U::PRE, act);
     }
+    T.sync();
+    normalise_run<F>(T, start, B, n, valid, jac, prefix, out, e, ebits);
 }
 
 // out[i] = affine(jac[i]) in the wire format (infinity -> all zero), one lane per point.

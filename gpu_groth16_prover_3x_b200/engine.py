@@ -61,6 +61,8 @@ def load_library():
     lib.b200msm_fold.argtypes = [vp, ci, vp, sz, vp]
     lib.b200msm_set_stream.argtypes = [vp, ci, vp]
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
+    lib.b200msm_set_table_budget.argtypes = [vp, sz]
+    lib.b200msm_bases_info.argtypes = [vp, ci, _u64p]
     lib.b200msm_last_timings.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), _u64p]
     lib.b200msm_microbench.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double)]
     lib.b200msm_selftest_field.argtypes = [vp, ci, ci, sz, vp, vp, vp]
@@ -238,12 +240,23 @@ class MsmContext:
 
     def last_timings(self, lane=0):
         ms = (ctypes.c_float * 6)()
-        info = (ctypes.c_uint64 * 5)()
+        info = (ctypes.c_uint64 * 8)()
         self._check(self.lib.b200msm_last_timings(self._h, lane, ms, info))
         d = {k: float(ms[i]) for i, k in enumerate(self.PHASES)}
         d.update(window_bits=int(info[0]), windows=int(info[1]), entries=int(info[2]),
-                 accumulate_launches=int(info[3]), kernel_launches=int(info[4]))
+                 accumulate_launches=int(info[3]), kernel_launches=int(info[4]), bucket_sets=int(info[5]),
+                 tables=int(info[6]))
         return d
+
+    def set_table_budget(self, max_bytes_per_set):
+        """Byte budget of the window tables built at upload time (0: none), see include/b200_msm.h."""
+        self._check(self.lib.b200msm_set_table_budget(self._h, max_bytes_per_set))
+
+    def bases_info(self, slot):
+        info = (ctypes.c_uint64 * 6)()
+        self._check(self.lib.b200msm_bases_info(self._h, slot, info))
+        return dict(points=int(info[0]), table_window_bits=int(info[1]), tables=int(info[2]), bucket_sets=int(info[3]),
+                    bytes=int(info[4]), table_build_ms=int(info[5]) / 1e3)
 
     def microbench(self, kind, iters=4096):
         g = ctypes.c_double()

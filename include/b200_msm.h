@@ -45,10 +45,19 @@ const char *b200msm_last_error(const b200msm_ctx *ctx);
 
 /* Upload a base set (A, B1, L, H queries: group G1; B2 query: group G2) and keep it resident in
  * HBM.  Replaces load_points_affine<EC>(31 * n, preprocessed_file) (reduce.cu:254-271,
- * cuda_prover_piecewise.cu:132-139): no 31x multiples table, no preprocessing file.
- * `affine` may be a host or device pointer.  Returns a slot id >= 0 in *slot. */
+ * cuda_prover_piecewise.cu:132-139) AND the reference's `main preprocess` step (main.cpp:311-339):
+ * instead of reading a 31x multiples table from a 25 GB file, the upload builds "window tables"
+ * 2^(c*G*t) * P_i (t < NT) on the device, inside the per-set byte budget, so that an MSM needs only
+ * G = ceil(windows / NT) bucket sets (one, with a full set of tables).  Sets of fewer than 256 points
+ * get no tables.  `affine` may be a host or device pointer.  Returns a slot id >= 0 in *slot. */
 int b200msm_bases_upload(b200msm_ctx *ctx, int group, const uint64_t *affine, size_t n, int *slot);
 int b200msm_bases_free(b200msm_ctx *ctx, int slot);
+/* Byte budget for the window tables of each base set uploaded afterwards (default 32 GiB; 0 = never
+ * build tables, every MSM then runs the plain one-bucket-set-per-window Pippenger). */
+int b200msm_set_table_budget(b200msm_ctx *ctx, size_t max_bytes_per_set);
+/* info[0] = points, [1] = window bits the tables were built for (0: none), [2] = tables NT,
+ * [3] = bucket sets G, [4] = bytes resident, [5] = table build time in microseconds. */
+int b200msm_bases_info(b200msm_ctx *ctx, int slot, uint64_t info[6]);
 
 /* result = sum_{i<n} scalars[i] * bases[offset + i] over the resident base set `slot`.
  * Replaces ec_reduce_straus<EC,C,R>(strm, out, multiples, scalars, N) (reduce.cu:131-152) and,
@@ -92,18 +101,22 @@ int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size
 int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream);
 
 /* Tuning / introspection. */
-int b200msm_set_window_bits(b200msm_ctx *ctx, int c); /* 0 = automatic */
+/* Window width for MSMs and for the tables of base sets uploaded afterwards; 0 = automatic.  An MSM
+ * whose forced width differs from the one its base set's tables were built for ignores the tables. */
+int b200msm_set_window_bits(b200msm_ctx *ctx, int c);
 /* Device time of the phases of the most recent completed MSM on `lane`, milliseconds, measured with
  * CUDA events on the launching stream: [0] total, [1] H2D scalars, [2] recode+sort,
  * [3] bucket accumulation (k_accumulate), [4] bucket reduction + window combine, [5] D2H result.
- * info[0] = window bits c, [1] = windows W, [2] = sorted entries, [3] = k_accumulate launches (1),
- * [4] = total kernel launches of the MSM. */
-int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[5]);
+ * info[0] = window bits c, [1] = signed digits (windows) per scalar, [2] = sorted entries,
+ * [3] = k_accumulate launches (1), [4] = total kernel launches of the MSM, [5] = bucket sets G,
+ * [6] = window tables used NT, [7] = reserved. */
+int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[8]);
 
 /* Synthetic microbenchmarks used by bench.py for the roofline denominator: runs `iters`
  * dependent-chain iterations of the named instruction mix on every SM and returns the achieved
  * rate in 10^9 operations per second (a 32x32->64 multiply-accumulate counts as one operation).
- * kind: 0 = IMAD.WIDE.U32 carry chains (the MSM's instruction), 1 = IMAD (mad.lo) only,
+ * kind: 0 = IMAD.WIDE.U32 (the 32x32->64 product the MSM is made of; half the rate of a 32-bit IMAD
+ *           on B200: 32 per clock per SM), 1 = IMAD (mad.lo, 64 per clock per SM),
  *       2 = the engine's own Fq Montgomery multiplication (32-bit CIOS on IMAD.WIDE.U32.X carry
  *           chains; returns 10^9 modmul/s),
  *       3 = the reduced-radix (29-bit limbs, carry-free IMAD.WIDE.U32) experiment, for comparison. */

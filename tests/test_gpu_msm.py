@@ -92,6 +92,46 @@ def test_degenerate_inputs(ctxs, oracle, curve, group):
     assert not out[24 * deg:].any()
 
 
+@pytest.mark.parametrize("curve,group", CG)
+def test_window_tables(ctxs, oracle, golden, curve, group):
+    """Window tables 2^(c*G*t) * P_i built at upload time (include/b200_msm.h): full set (one bucket set),
+    partial set under a byte budget (1 < G < windows), and none; infinity bases stay infinity in every
+    table; sub-ranges index all tables with the same offset."""
+    z = golden["msm_vectors"]
+    key = "c%d_g%d" % (curve, group)
+    deg = po.degree(curve, group)
+    bases, sc = z[key + "_bases"], z[key + "_scalars"]
+    nb = len(bases) // (24 * deg)
+    assert nb >= 257
+    ctx = ctxs[curve]
+    point_bytes = 2 * deg * 96
+    try:
+        for c, budget, want_sets in ((0, 1 << 40, "one"), (7, 5 * nb * point_bytes, "some"), (9, 0, "all"), (11, 1 << 40, "one")):
+            ctx.set_window_bits(c)
+            ctx.set_table_budget(budget)
+            slot = ctx.upload_bases(group, bases)
+            info = ctx.bases_info(slot)
+            if want_sets == "one":
+                assert info["bucket_sets"] == 1 and info["tables"] > 1
+            elif want_sets == "some":
+                assert info["tables"] == 5 and 1 < info["bucket_sets"] < 108
+            else:
+                assert info["tables"] == 1
+            for n in (257, 100, 1):
+                got = affine(oracle, curve, group, ctx.msm(slot, sc[:n * 12], n))
+                assert (got == z["%s_n%d_out" % (key, n)]).all(), (c, budget, n)
+                t = ctx.last_timings()
+                assert t["tables"] == info["tables"]
+            off, n = 3, 200
+            want, _ = oracle.msm(curve, group, bases[off * 24 * deg:(off + n) * 24 * deg], sc[off * 12:(off + n) * 12])
+            got = affine(oracle, curve, group, ctx.msm(slot, sc[off * 12:(off + n) * 12], n, offset=off))
+            assert (got == want).all(), (c, budget)
+            ctx.free_bases(slot)
+    finally:
+        ctx.set_window_bits(0)
+        ctx.set_table_budget(32 << 30)
+
+
 def test_async_lanes_and_shards(ctxs, oracle):
     """Four MSMs in flight on four lanes (A, B1, L on G1; B2 on G2), then the point-range sharding
     identity: the fold of per-shard partials equals the unsharded MSM."""
