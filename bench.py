@@ -152,7 +152,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
     import gpu_groth16_prover_3x_b200 as pkg
-    from gpu_groth16_prover_3x_b200 import synthetic
+    from gpu_groth16_prover_3x_b200 import sharding, synthetic
 
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -225,11 +225,7 @@ def run_b200(args):
     e2e_s, e2e_wall, _, out_host, _ = timed(host_sets, args.steps)
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.max_over_ranks(x, device="cuda")
 
     dev_s, e2e_s = max_over_ranks(dev_s), max_over_ranks(e2e_s)
     dev_wall, e2e_wall = max_over_ranks(dev_wall), max_over_ranks(e2e_wall)
@@ -237,12 +233,10 @@ def run_b200(args):
     # fold of the per-rank partial points (outside the timed region of the shards: it is 864 B per rank)
     fold_ms = None
     if world > 1:
-        part = torch.from_numpy(out_dev.view(np.int64)).cuda()
-        gathered = [torch.empty_like(part) for _ in range(world)]
-        dist.all_gather(gathered, part)
+        partials = sharding.gather_partials(out_dev, device="cuda")
         if rank == 0:
             t0 = time.perf_counter()
-            ctx.fold(group, np.concatenate([g.cpu().numpy().view(np.uint64) for g in gathered]))
+            ctx.fold(group, partials)
             fold_ms = (time.perf_counter() - t0) * 1e3
 
     if rank != 0:
