@@ -251,7 +251,11 @@ def run_b200(args):
     info = phases[-1]
     acc_ms = statistics.mean(p["accumulate"] for p in phases)
     W = info["windows"]
-    macs_per_launch = float(n) * W * 11 * k_tower * 1176  # one mixed add per point and window
+    # executed work of the accumulation phase: one addition per sorted entry (minus one per non-empty bucket,
+    # neglected); 6 field multiplications per batched-affine addition, 11 per Jacobian mixed addition
+    # (SURVEY.md 8(d)); a field multiplication in the degree-k tower is k_tower Fq products of 1176 MAC
+    muls_per_add = 6 if info.get("accumulator", 0) == 0 else 11
+    macs_per_launch = float(n) * W * muls_per_add * k_tower * 1176
     achieved = macs_per_launch / (acc_ms * 1e-3) / 1e9
     micro = {"imad_wide_gmacs": ctx.microbench(0, 4096), "imad_lo_gops": ctx.microbench(1, 4096),
              "fq_modmul_gmuls": ctx.microbench(2, 2048)}
@@ -263,7 +267,8 @@ def run_b200(args):
     # reference-style algorithm would have to execute to deliver the same points/s
     canonical_macs_per_point = 1176.0 * 11 * k_tower * 48
     roofline = {
-        "kernel": "k_accumulate", "bound": "imad", "achieved": achieved, "peak": peak, "unit": "GMAC/s", "frac": achieved / peak,
+        "kernel": "k_batch_add (all rounds of one MSM)" if muls_per_add == 6 else "k_accumulate", "bound": "imad",
+        "field_muls_per_addition": muls_per_add, "achieved": achieved, "peak": peak, "unit": "GMAC/s", "frac": achieved / peak,
         "traffic": None, "launch_ms": acc_ms, "share_of_step": acc_ms / (dev_s / args.steps * 1e3),
         "peak_source": "measured in this run: max(IMAD.WIDE.U32 stream, Fq Montgomery product in registers x 1176 MAC); "
                        "a 32x32->64 multiply-add issues at 32 per clock per SM on B200 (tools/pipe_probe.cu)",

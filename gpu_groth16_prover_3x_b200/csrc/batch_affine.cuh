@@ -1,0 +1,387 @@
+// Batched-affine bucket accumulation (replaces the per-lane Jacobian chains of k_accumulate and the
+// edge fold; the reference's counterpart is the Straus kernel + pairwise tree, multiexp/reduce.cu:11-127).
+//
+// The sorted list of (bucket, point) entries is reduced by ROUNDS of pairwise AFFINE additions:
+// a bucket holding k points holds ceil(k/2) after a round, so every bucket is down to one point after
+// ceil(log2(max occupancy)) rounds and the total number of additions is the same sum_b (k_b - 1) as a
+// serial chain.  An affine addition costs one field inversion; Montgomery's simultaneous inversion
+// shares ONE inversion among all the additions of a tile (32 lanes x B additions):
+//
+//   forward   d_i = x2 - x1 (or 2 y1 when doubling, 1 when there is nothing to add);  prefix products
+//   tile      product over the 32 lanes (xor butterfly), one binary-gcd inversion by one thread,
+//             each lane's own inverse = inverse of the tile product x product of the other lanes
+//   backward  1/d_i = inv * prefix_i;  inv *= d_i;  lambda = (y2 - y1)/d_i;  x3, y3
+//
+// = 6 field multiplications per addition (1 forward, 5 backward) + 10 per lane and tile, against 11
+// (8M + 3S) for the Jacobian mixed addition.  Prefix products are parked in the x-half of the output
+// slot of the same addition, so the round needs no scratch of its own.
+//
+// Per round r:   k_scan_halve* (next offsets = scan of ceil(k/2))  ->  k_plan (source rows of every
+// output point; binary search of its bucket)  ->  k_batch_add (the additions, persistent tiles).
+// Round 0 reads the window tables through the sorted entry list (row | sign << 31); later rounds read
+// the previous round's output.  Rounds after the last useful one exit on a device-side flag, so the host
+// enqueues a fixed worst-case number of rounds without ever synchronising.
+#pragma once
+#ifdef MNT753_HOST_EMU
+#include "curves.cuh"
+#else
+#include "msm_kernels.cuh"
+#endif
+
+namespace mnt753 {
+
+constexpr uint32_t BA_NONE = 0xffffffffu;
+constexpr int BA_BMAX = 64;  // additions per lane and tile
+enum : uint32_t { BA_NORMAL = 0, BA_DBL = 1, BA_CANCEL = 2, BA_COPY1 = 3, BA_IDLE = 4 };
+
+struct BaSlots { int X1, Y1, X2, Y2, INV, PRE, D, T; };
+
+// Phase 1 of one addition: slots X1, X2 hold the abscissae (X2 only where has2).  Computes the
+// denominator D and classifies the pair.  load_y(pred) must bring (signed) Y1, Y2 into their slots for
+// the lanes with pred; it is called only when some lane has x1 == x2.
+template <class F, class LoadY>
+MSM_DEVICE uint32_t pair_forward(const Team<F> &T, const BaSlots &s, bool valid, bool has2, LoadY load_y) {
+    T.sub(s.D, s.X2, s.X1);
+    const bool dz = T.is_zero(s.D);
+    const bool need_y = has2 && dz;
+    uint32_t code = !valid ? BA_IDLE : (!has2 ? BA_COPY1 : BA_NORMAL);
+    if (team_any(need_y)) {
+        load_y(need_y);
+        T.sub(s.T, s.Y2, s.Y1);
+        const bool eq = T.is_zero(s.T);
+        const bool y0 = T.is_zero(s.Y1);   // a point of order two doubles to infinity
+        const bool dbl = need_y && eq && !y0;
+        if (need_y) code = dbl ? BA_DBL : BA_CANCEL;
+        T.dbl(s.D, s.Y1, dbl);
+    }
+    T.set_one(s.D, code >= BA_CANCEL);
+    return code;
+}
+
+// Phase 2: slots X1, Y1, X2, Y2 hold the (signed) operands, PRE the prefix product, INV the running
+// inverse.  Leaves the sum in (X2, Y2) and advances INV.  Returns true when the result is infinity.
+template <class F>
+MSM_DEVICE bool pair_backward(const Team<F> &T, const BaSlots &s, uint32_t code, bool a_inf) {
+    const bool dbl = code == BA_DBL;
+    const bool any_dbl = team_any(dbl);
+    T.sub(s.D, s.X2, s.X1);
+    if (any_dbl) T.dbl(s.D, s.Y1, dbl);
+    T.set_one(s.D, code >= BA_CANCEL);
+    T.mul(s.PRE, s.INV, s.PRE);          // 1 / d
+    T.mul(s.INV, s.INV, s.D);            // inverse of the shorter prefix
+    T.sub(s.Y2, s.Y2, s.Y1);             // numerator
+    if (any_dbl) {                       // 3 x1^2 + a
+        T.sqr(s.T, s.X1);
+        T.dbl(s.D, s.T);
+        T.add(s.T, s.T, s.D);
+        T.set_one(s.D);
+        T.mul_by_a(s.D, s.D);
+        T.add(s.Y2, s.T, s.D, dbl);
+    }
+    T.mul(s.D, s.Y2, s.PRE);             // lambda
+    T.add(s.X2, s.X1, s.X2);
+    T.sqr(s.PRE, s.D);
+    T.sub(s.X2, s.PRE, s.X2);            // x3 = lambda^2 - x1 - x2
+    T.sub(s.PRE, s.X1, s.X2);
+    T.mul(s.PRE, s.D, s.PRE);
+    T.sub(s.Y2, s.PRE, s.Y1);            // y3 = lambda (x1 - x3) - y1
+    const bool copy1 = code == BA_COPY1, cancel = code == BA_CANCEL;
+    T.copy(s.X2, s.X1, copy1);
+    T.copy(s.Y2, s.Y1, copy1);
+    T.set_zero(s.X2, cancel);
+    T.set_zero(s.Y2, cancel);
+    return cancel || (copy1 && a_inf);
+}
+
+// After the forward pass INV holds each lane's product of denominators.  Replace it by the lane's own
+// inverse: xor-butterfly product over the 32 lanes, one inversion (lane 0), own = tile^-1 * others.
+// Scratch: S, A, B, C (four distinct slots, all free between the passes).
+template <class F>
+MSM_DEVICE void tile_inverse(const Team<F> &T, int INV, int S, int A, int B, int C) {
+#ifdef MNT753_HOST_EMU
+    T.inv_lane0(A, INV, B, C);
+    T.copy(INV, A);
+#else
+    const int lane = T.lane();
+    for (int m = 1; m < 32; m <<= 1) {
+        T.copy_lane(A, INV, lane ^ m);
+        if (m == 1) T.copy(S, A); else T.mul(S, S, A);
+        T.mul(INV, INV, A);
+    }
+    T.inv_lane0(A, INV, B, C);
+    T.copy_lane(B, A, 0);
+    T.mul(INV, B, S);
+#endif
+}
+
+#ifndef MNT753_HOST_EMU
+// ------------------------------------------------------------------------------------------------
+struct BaArgs {
+    uint32_t K;                 // buckets (all sets)
+    uint32_t round;
+    const uint32_t *off_cur;    // K + 1 offsets of the round's input list
+    uint32_t *off_next;         // K + 1 offsets of its output list
+    const uint32_t *entries;    // round 0: sorted (row | sign << 31)
+    const uint32_t *bases;      // round 0: window tables
+    const uint32_t *in_pts;     // round > 0: previous output (affine AoS)
+    const uint8_t *in_inf;
+    uint32_t *out_pts;
+    uint8_t *out_inf;
+    uint4 *pairs;               // the round's additions: (source 0, source 1, output index, -)
+    uint32_t *npairs;           // [rounds]
+    uint32_t *maxcnt;           // [rounds + 1] largest bucket occupancy entering each round
+    uint32_t *tile_counter;     // [rounds]
+    uint32_t *nrounds;          // rounds actually executed
+    uint32_t *bsum;             // scan scratch
+    uint32_t nscan;
+};
+
+__device__ __forceinline__ bool ba_round_active(const BaArgs &a) { return a.round == 0 || a.maxcnt[a.round] > 1u; }
+
+// offsets of the next round: exclusive scan of ceil(k / 2); also records the largest k of this round.
+// (Three launches, same structure as k_scan_local / k_scan_bsum / k_scan_add.)
+static __global__ void __launch_bounds__(SCAN_T) k_ba_scan_local(BaArgs a) {
+    __shared__ uint32_t sh[SCAN_T];
+    __shared__ uint32_t smax;
+    if (a.round > 0 && a.maxcnt[a.round - 1] <= 1u) return;   // previous round did not run: nothing left
+    if (threadIdx.x == 0) smax = 0;
+    uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
+    uint32_t v[SCAN_E], s = 0, mx = 0;
+    for (int e = 0; e < SCAN_E; ++e) {
+        uint32_t k = (base + e < a.K) ? a.off_cur[base + e + 1] - a.off_cur[base + e] : 0u;
+        mx = max(mx, k);
+        v[e] = (k + 1u) >> 1;
+        s += v[e];
+    }
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    atomicMax(&smax, mx);
+    for (int d = 1; d < SCAN_T; d <<= 1) {
+        uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
+        __syncthreads();
+        sh[threadIdx.x] += t;
+        __syncthreads();
+    }
+    uint32_t excl = sh[threadIdx.x] - s;
+    for (int e = 0; e < SCAN_E; ++e) { if (base + e < a.K) a.off_next[base + e] = excl; excl += v[e]; }
+    if (threadIdx.x == SCAN_T - 1) a.bsum[blockIdx.x] = sh[SCAN_T - 1];
+    if (threadIdx.x == 0) atomicMax(&a.maxcnt[a.round], smax);
+}
+static __global__ void __launch_bounds__(SCAN_T) k_ba_scan_bsum(BaArgs a) {
+    if (!ba_round_active(a)) return;
+    __shared__ uint32_t sh[SCAN_T];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < a.nscan; base += SCAN_T) {
+        uint32_t i = base + threadIdx.x;
+        uint32_t s = (i < a.nscan) ? a.bsum[i] : 0u;
+        sh[threadIdx.x] = s;
+        __syncthreads();
+        for (int d = 1; d < SCAN_T; d <<= 1) {
+            uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < a.nscan) a.bsum[i] = carry + sh[threadIdx.x] - s;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[SCAN_T - 1];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) a.off_next[a.K] = carry;
+}
+static __global__ void __launch_bounds__(SCAN_T) k_ba_scan_add(BaArgs a) {
+    if (!ba_round_active(a)) return;
+    uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
+    uint32_t add = a.bsum[blockIdx.x];
+    for (int e = 0; e < SCAN_E; ++e)
+        if (base + e < a.K) a.off_next[base + e] += add;
+}
+
+// Plan of a round.  For every output point j: its bucket b (binary search in off_next), local index l, and
+// its inputs off_cur[b] + 2l (+ 1 when the bucket still has a partner for it).  Real additions are appended
+// to the round's pair list (warp-aggregated atomic; order is irrelevant, each pair carries its output
+// index); an input without a partner -- or whose partner is infinity -- is copied to its output slot right
+// here, so that the arithmetic kernel sees additions only.
+//   round 0 : sources are sorted entries (table row | sign << 31), never infinity (filtered by the sort)
+//   later   : sources are indices into the previous round's output, with its infinity flags
+template <class G, bool FIRST>
+__global__ void __launch_bounds__(256) k_ba_plan(BaArgs a) {
+    typedef typename G::F F;
+    typedef typename F::M M;
+    constexpr int DEG = F::DEG, EW = DEG * NLIMB, AFFW = 2 * EW;
+    if (!ba_round_active(a)) return;
+    const uint32_t E = a.off_next[a.K];
+    const uint32_t *in = FIRST ? a.bases : a.in_pts;
+    const int lane = threadIdx.x & 31;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t iters = (E + stride - 1) / stride;
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t j = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = j < E;
+        uint32_t s0 = 0, s1 = BA_NONE;
+        bool s0_inf = false;
+        if (valid) {
+            const uint32_t b = bucket_of(a.off_next, a.K, j);
+            const uint32_t l = j - a.off_next[b];
+            const uint32_t lo = a.off_cur[b], cnt = a.off_cur[b + 1] - lo;
+            const uint32_t i0 = lo + 2u * l;
+            const bool has2 = 2u * l + 1u < cnt;
+            if (FIRST) {
+                s0 = a.entries[i0];
+                if (has2) s1 = a.entries[i0 + 1];
+            } else {
+                const bool inf0 = a.in_inf[i0] != 0;
+                const bool inf1 = has2 ? a.in_inf[i0 + 1] != 0 : true;
+                if (has2 && !inf0 && !inf1) { s0 = i0; s1 = i0 + 1; }
+                else if (has2 && inf0 && !inf1) s0 = i0 + 1;
+                else { s0 = i0; s0_inf = inf0; }
+            }
+        }
+        const bool is_pair = valid && s1 != BA_NONE;
+        const unsigned m = __ballot_sync(0xffffffffu, is_pair);
+        uint32_t base = 0;
+        if (lane == 0 && m) base = atomicAdd(a.npairs + a.round, (uint32_t)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (is_pair) a.pairs[base + __popc(m & ((1u << lane) - 1u))] = make_uint4(s0, s1, j, 0u);
+        if (valid && !is_pair) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(in + (size_t)(s0 & 0x7fffffffu) * AFFW);
+            uint4 *dst = reinterpret_cast<uint4 *>(a.out_pts + (size_t)j * AFFW);
+#pragma unroll
+            for (int q = 0; q < DEG * QUADS; ++q) dst[q] = src[q];
+            const bool neg = FIRST && (s0 >> 31);
+#pragma unroll
+            for (int c = 0; c < DEG; ++c) {
+                fq_t y, ny;
+#pragma unroll
+                for (int q = 0; q < QUADS; ++q) { uint4 v = src[(DEG + c) * QUADS + q]; y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w; }
+                if (neg) { fq_neg<M>(ny, y);
+#pragma unroll
+                    for (int i = 0; i < NLIMB; ++i) y[i] = ny[i]; }
+#pragma unroll
+                for (int q = 0; q < QUADS; ++q) { uint4 v; v.x = y[4 * q]; v.y = y[4 * q + 1]; v.z = y[4 * q + 2]; v.w = y[4 * q + 3]; dst[(DEG + c) * QUADS + q] = v; }
+            }
+            a.out_inf[j] = s0_inf ? 1 : 0;
+        }
+    }
+}
+
+template <class G>
+struct BaCfg {
+    static constexpr int DEG = G::F::DEG;
+    static constexpr int NSLOT = 8;
+    static constexpr int TPB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 1);
+    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 3);
+    typedef TeamSetup<G, NSLOT, TPB> TS;
+};
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+// one coordinate (96 * DEG bytes) of the point whose first word is g: the caller's coefficient only
+template <class F>
+__device__ __forceinline__ void prefetch_coord(const Team<F> &T, const uint32_t *g) {
+    const char *p = reinterpret_cast<const char *>(g) + T.comp * (NLIMB * 4);
+    prefetch_l2(p);
+    prefetch_l2(p + NLIMB * 4 - 4);
+}
+
+template <class G, bool FIRST>
+__global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch_add(BaArgs a) {
+    typedef typename G::F F;
+    typedef BaCfg<G> C;
+    constexpr int DEG = F::DEG;
+    constexpr int EW = DEG * NLIMB, AFFW = 2 * EW;
+    if (!ba_round_active(a)) return;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    __shared__ uint32_t s_tile[C::TPB];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    const int lane = threadIdx.x & 31;
+    const BaSlots s = {0, 1, 2, 3, 4, 5, 6, 7};
+    const uint32_t *in = FIRST ? a.bases : a.in_pts;
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) *a.nrounds = a.round + 1;
+    const uint32_t E = a.npairs[a.round];
+    // additions per lane and tile: enough tiles to give every resident team a few
+    const uint32_t teams = gridDim.x * C::TPB;
+    uint32_t B = (E + teams * 32u * 3u - 1u) / (teams * 32u * 3u);
+    B = B < 1u ? 1u : (B > (uint32_t)BA_BMAX ? (uint32_t)BA_BMAX : B);
+    const uint32_t per_tile = 32u * B;
+    const uint32_t ntiles = (E + per_tile - 1u) / per_tile;
+    const uint4 idle = make_uint4(0u, 0u, 0u, 0u);
+
+    for (;;) {
+        T.sync();
+        if (T.comp == 0 && lane == 0) s_tile[team] = atomicAdd(a.tile_counter + a.round, 1u);
+        T.sync();
+        const uint32_t tile = s_tile[team];
+        if (tile >= ntiles) break;
+        const uint32_t base = tile * per_tile;
+
+        // ---- forward: denominators and prefix products
+        T.set_one(s.INV);
+        uint4 nxt = (base + lane < E) ? a.pairs[base + lane] : idle;
+        for (uint32_t i = 0; i < B; ++i) {
+            const uint32_t p = base + i * 32u + lane;
+            const bool valid = p < E;
+            const uint4 d = nxt;
+            const uint32_t r1 = d.x & 0x7fffffffu, r2 = d.y & 0x7fffffffu, j = d.z;
+            if (i + 1 < B) {   // next step's sources: descriptor now, coordinates into L2
+                const uint32_t pn = p + 32u;
+                nxt = (pn < E) ? a.pairs[pn] : idle;
+                if (pn < E) {
+                    prefetch_coord(T, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW);
+                    prefetch_coord(T, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW);
+                }
+            }
+            g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
+            g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
+            const uint32_t code = pair_forward(T, s, valid, valid, [&](bool pred) {
+                g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, pred);
+                g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, pred);
+                if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, pred); T.neg_if(s.Y2, s.Y2, d.y >> 31, pred); }
+            });
+            if (valid && T.comp == 0) a.out_inf[j] = (uint8_t)code;   // parked until the backward pass
+            s2g(T, a.out_pts + (size_t)j * AFFW, s.INV, valid);       // exclusive prefix, parked in the output slot
+            T.mul(s.INV, s.INV, s.D);
+        }
+        // ---- one inversion for the whole tile
+        tile_inverse(T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
+        // ---- backward: the additions
+        {
+            const uint32_t pl = base + (B - 1u) * 32u + lane;
+            nxt = (pl < E) ? a.pairs[pl] : idle;
+        }
+        for (int i = (int)B - 1; i >= 0; --i) {
+            const uint32_t p = base + (uint32_t)i * 32u + lane;
+            const bool valid = p < E;
+            const uint4 d = nxt;
+            const uint32_t r1 = d.x & 0x7fffffffu, r2 = d.y & 0x7fffffffu, j = d.z;
+            if (i > 0) {
+                const uint32_t pn = p - 32u;     // pn < p; valid whenever any later index of the lane is
+                nxt = (pn < E) ? a.pairs[pn] : idle;
+                if (pn < E) {
+                    const uint32_t *n1 = in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, *n2 = in + (size_t)(nxt.y & 0x7fffffffu) * AFFW;
+                    prefetch_coord(T, n1); prefetch_coord(T, n1 + EW);
+                    prefetch_coord(T, n2); prefetch_coord(T, n2 + EW);
+                    prefetch_coord(T, a.out_pts + (size_t)nxt.z * AFFW);
+                }
+            }
+            const uint32_t code = valid ? a.out_inf[j] : (uint32_t)BA_IDLE;
+            g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
+            g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);
+            g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
+            g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
+            g2s(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
+            if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, valid); T.neg_if(s.Y2, s.Y2, d.y >> 31, valid); }
+            const bool res_inf = pair_backward(T, s, code, false);
+            s2g(T, a.out_pts + (size_t)j * AFFW, s.X2, valid);
+            s2g(T, a.out_pts + (size_t)j * AFFW + EW, s.Y2, valid);
+            if (valid && T.comp == 0) a.out_inf[j] = res_inf ? 1 : 0;
+        }
+    }
+}
+#endif  // !MNT753_HOST_EMU
+
+}  // namespace mnt753

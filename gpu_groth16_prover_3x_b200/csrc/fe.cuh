@@ -26,6 +26,14 @@ namespace mnt753 {
 constexpr int QUADS = 6;    // uint4 per Fq element
 constexpr int LANES = 32;
 
+// Slot operations are real functions on the device (one copy each): the unrolled 24-limb bodies would
+// otherwise be replicated at every call site and push the hot loops out of the instruction cache.
+#ifdef MNT753_HOST_EMU
+#define MSM_OP inline
+#else
+#define MSM_OP __device__ __noinline__
+#endif
+
 #ifdef MNT753_HOST_EMU
 #define MSM_FOR_COMP(c) for (int c = 0; c < DEG; ++c)
 #define MSM_NCOMP DEG
@@ -35,6 +43,16 @@ constexpr int LANES = 32;
 #define MSM_NCOMP 1
 #define MSM_CI(c) 0
 #endif
+
+// cube roots of unity for the Frobenius map of Fq3 = Fq[u]/(u^3 - 11) (only MNT6753's base field has one)
+template <class M> struct Frob3 {
+    MSM_HD static constexpr uint32_t W1(int j) { return j == 0 ? 1u : 0u; }
+    MSM_HD static constexpr uint32_t W2(int j) { return j == 0 ? 1u : 0u; }
+};
+template <> struct Frob3<ModB> {
+    MSM_HD static constexpr uint32_t W1(int j) { constexpr uint32_t t[NLIMB] = MNT753_FROB3_W1_B_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t W2(int j) { constexpr uint32_t t[NLIMB] = MNT753_FROB3_W2_B_U32; return t[j]; }
+};
 
 // Field configuration: M = base modulus, DEG = tower degree, NR = non-residue,
 // AKIND selects the curve-coefficient multiplication (mul_by_a):
@@ -116,17 +134,17 @@ struct Team {
     }
     MSM_DEVICE void sqr(int d, int a, bool pred = true) const { mul(d, a, a, pred); }
 
-    MSM_DEVICE void add(int d, int a, int b, bool pred = true) const {
+    MSM_OP void add(int d, int a, int b, bool pred = true) const {
         MSM_FOR_COMP(c) { fq_t x, y; ld(x, a, c); ld(y, b, c); fq_add<M>(x, x, y); st(d, c, x, pred); }
     }
-    MSM_DEVICE void sub(int d, int a, int b, bool pred = true) const {
+    MSM_OP void sub(int d, int a, int b, bool pred = true) const {
         MSM_FOR_COMP(c) { fq_t x, y; ld(x, a, c); ld(y, b, c); fq_sub<M>(x, x, y); st(d, c, x, pred); }
     }
-    MSM_DEVICE void dbl(int d, int a, bool pred = true) const {
+    MSM_OP void dbl(int d, int a, bool pred = true) const {
         MSM_FOR_COMP(c) { fq_t x; ld(x, a, c); fq_add<M>(x, x, x); st(d, c, x, pred); }
     }
     // d = neg ? -a : a   (per lane)
-    MSM_DEVICE void neg_if(int d, int a, bool neg, bool pred = true) const {
+    MSM_OP void neg_if(int d, int a, bool neg, bool pred = true) const {
         MSM_FOR_COMP(c) {
             fq_t x, y; ld(x, a, c); fq_neg<M>(y, x);
 #pragma unroll
@@ -134,7 +152,7 @@ struct Team {
             st(d, c, x, pred);
         }
     }
-    MSM_DEVICE void copy(int d, int a, bool pred = true) const {
+    MSM_OP void copy(int d, int a, bool pred = true) const {
         MSM_FOR_COMP(c) { fq_t x; ld(x, a, c); st(d, c, x, pred); }
     }
     MSM_DEVICE void set_zero(int d, bool pred = true) const {
@@ -151,7 +169,7 @@ struct Team {
     }
 
     // d = coeff_a * x  (see FieldCfg::AKIND)
-    MSM_DEVICE void mul_by_a(int d, int x, bool pred = true) const {
+    MSM_OP void mul_by_a(int d, int x, bool pred = true) const {
         fq_t res[MSM_NCOMP];
         sync();
         MSM_FOR_COMP(c) {
@@ -169,8 +187,78 @@ struct Team {
         MSM_FOR_COMP(c) st(d, c, res[MSM_CI(c)], pred);
     }
 
+
+    // ---- cross-lane access and inversion (batched-affine accumulation, batch_affine.cuh) ----------
+    MSM_DEVICE int lane() const {
+#ifdef MNT753_HOST_EMU
+        return 0;
+#else
+        return threadIdx.x & 31;
+#endif
+    }
+    // d (this lane) = a of lane `src`.  Barriers on both sides: other lanes' data must be settled before
+    // the read, and every read must be over before a later write to `a`.
+    MSM_OP void copy_lane(int d, int a, int src) const {
+        fq_t x[MSM_NCOMP];
+        sync();
+        MSM_FOR_COMP(c) {
+            const uint4 *p = elem(a, c) - lane() + src;
+#pragma unroll
+            for (int q = 0; q < QUADS; ++q) {
+                uint4 v = p[q * LANES];
+                x[MSM_CI(c)][4 * q] = v.x; x[MSM_CI(c)][4 * q + 1] = v.y; x[MSM_CI(c)][4 * q + 2] = v.z; x[MSM_CI(c)][4 * q + 3] = v.w;
+            }
+        }
+        sync();
+        MSM_FOR_COMP(c) st(d, c, x[MSM_CI(c)]);
+    }
+    // conjugate-like maps whose product with a is the norm to Fq:  Fq2: (a0, -a1);  Fq3: Frobenius^k,
+    // (a0, a1 w^k, a2 w^2k) with w = 11^((q-1)/3).  Own coefficient only.
+    MSM_OP void frob(int d, int a, int k) const {
+        MSM_FOR_COMP(c) {
+            fq_t x, y;
+            ld(x, a, c);
+            if (DEG == 2) {
+                if (c == 1) { fq_neg<M>(y, x); st(d, c, y); } else st(d, c, x);
+            } else if (DEG == 3) {
+                const int e = (c * k) % 3;
+                if (e == 0) st(d, c, x);
+                else {
+                    fq_t w;
+#pragma unroll
+                    for (int i = 0; i < NLIMB; ++i) w[i] = (e == 1) ? Frob3<M>::W1(i) : Frob3<M>::W2(i);
+                    fq_mul<M>(y, x, w);
+                    st(d, c, y);
+                }
+            } else st(d, c, x);
+        }
+    }
+    // d = 1 / a for the element of LANE 0 only (other lanes: unspecified); a != 0.  t0, t1 scratch, all
+    // four slots distinct.  One binary-gcd inversion in Fq by a single thread; for the towers the element is
+    // first reduced to its norm:  a^-1 = conj(a) / N(a),  conj(a) = prod of the non-trivial Frobenius images.
+    MSM_OP void inv_lane0(int d, int a, int t0, int t1) const {
+        if (DEG == 1) {
+            MSM_FOR_COMP(c) {
+                if (lane() == 0) { fq_t x, r; ld(x, a, c); fq_inv<M>(r, x); st(d, c, r); }
+            }
+#ifndef MNT753_HOST_EMU
+            __syncwarp();
+#endif
+            return;
+        }
+        frob(t0, a, 1);
+        if (DEG == 3) { frob(t1, a, 2); mul(t0, t0, t1); }
+        mul(t1, a, t0);                      // norm, lies in Fq: (N, 0[, 0])
+#ifdef MNT753_HOST_EMU
+        { fq_t x, r; ld(x, t1, 0); fq_inv<M>(r, x); st(t1, 0, r); }
+#else
+        if (comp == 0 && lane() == 0) { fq_t x, r; ld(x, t1, 0); fq_inv<M>(r, x); st(t1, 0, r); }
+#endif
+        mul(d, t0, t1);
+    }
+
     // per-lane test, identical in every warp of the team
-    MSM_DEVICE bool is_zero(int e) const {
+    MSM_OP bool is_zero(int e) const {
 #ifdef MNT753_HOST_EMU
         bool z = true;
         for (int c = 0; c < DEG; ++c) { fq_t x; ld(x, e, c); z = z && fq_is_zero(x); }

@@ -3,6 +3,7 @@
 // builds in parallel; msm.cu reaches them through the GroupOps table.
 #pragma once
 #include "host_ctx.cuh"
+#include "batch_affine.cuh"
 
 namespace {
 
@@ -44,10 +45,30 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     p.bsum = (uint32_t *)take((size_t)p.nscan * 4);
     a.group_counter = (uint32_t *)take(4);
     a.entries = (uint32_t *)take((size_t)emax * 4 + 4);
-    a.buckets = (uint32_t *)take((size_t)a.K * JACB);
-    a.edges = (uint32_t *)take((size_t)a.max_chunks * 2 * JACB);
-    a.edge_bucket = (uint32_t *)take((size_t)a.max_chunks * 2 * 4);
-    {
+    if (ctx->accumulator == 0) {
+        // batched-affine rounds: a round halves every bucket (rounding up), so its output has at most
+        // (S + min(K, S)) / 2 points for an input of S
+        constexpr size_t AFFB = 2 * G::F::DEG * NLIMB * 4;
+        uint64_t s1 = (emax + std::min<uint64_t>(a.K, emax) + 1) / 2, s2 = (s1 + std::min<uint64_t>(a.K, s1) + 1) / 2;
+        p.ba_cap[0] = s1 + 1;
+        p.ba_cap[1] = s2 + 1;
+        // occupancy of a bucket is at most n * (digits per bucket set)
+        const uint64_t occ = (uint64_t)n * ((a.Wd + a.W - 1) / a.W);
+        p.ba_rounds = 1;
+        while ((1ull << p.ba_rounds) < occ) ++p.ba_rounds;
+        for (int i = 0; i < 2; ++i) {
+            a.ba_pts[i] = (uint32_t *)take(p.ba_cap[i] * AFFB);
+            a.ba_inf[i] = (uint8_t *)take(p.ba_cap[i]);
+        }
+        a.ba_off[0] = a.offs;
+        a.ba_off[1] = (uint32_t *)take(((size_t)a.K + 1) * 4);
+        p.ba_pairs = (uint4 *)take((emax / 2 + 1) * 16);
+        p.ba_ctl = (uint32_t *)take((size_t)(3 * p.ba_rounds + 4) * 4);   // nrounds | maxcnt[R + 1] | tile_counter[R] | npairs[R]
+        a.ba_nrounds = p.ba_ctl;
+    } else {
+        a.buckets = (uint32_t *)take((size_t)a.K * JACB);
+        a.edges = (uint32_t *)take((size_t)a.max_chunks * 2 * JACB);
+        a.edge_bucket = (uint32_t *)take((size_t)a.max_chunks * 2 * 4);
         const size_t n1 = (a.max_chunks + FOLD_GS - 1) / FOLD_GS, n2 = (n1 + FOLD_GS - 1) / FOLD_GS;
         a.fold_pts[0] = (uint32_t *)take(n1 * 2 * JACB);
         a.fold_key[0] = (uint32_t *)take(n1 * 2 * 4);
@@ -126,7 +147,10 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
 
     if ((rc = set_smem(ctx, k_accumulate<G>, AC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_fold_edges<G>, TC::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_bucket_reduce<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_bucket_reduce<G, false>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_bucket_reduce<G, true>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_batch_add<G, false>, BaCfg<G>::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_batch_add<G, true>, BaCfg<G>::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_sum<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_horner<G>, TC::TS::SMEM))) return rc;
 
@@ -146,14 +170,55 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     launches += 6;
     CU(cudaEventRecord(ln.ev[2], st));
 
-    CU(cudaMemsetAsync(a.group_counter, 0, 4, st));
-    CU(cudaMemsetAsync(a.edge_bucket, 0xff, (size_t)a.max_chunks * 2 * 4, st));
-    k_accumulate<G><<<ctx->sm_count * AC::MINB, AC::TS::THREADS, AC::TS::SMEM, st>>>(a);
-    launches += 1;
-    CU(cudaEventRecord(ln.ev[3], st));
-
     const unsigned tail_lanes = TC::TPB * 32;
-    {
+    const bool batched = ctx->accumulator == 0;
+    uint64_t acc_launches = 0;
+    if (batched) {
+        typedef BaCfg<G> BC;
+        CU(cudaMemsetAsync(p.ba_ctl, 0, (size_t)(3 * p.ba_rounds + 4) * 4, st));
+        BaArgs b;
+        memset(&b, 0, sizeof b);
+        b.K = a.K;
+        b.entries = a.entries;
+        b.bases = a.bases;
+        b.pairs = p.ba_pairs;
+        b.nrounds = p.ba_ctl;
+        b.maxcnt = p.ba_ctl + 1;
+        b.tile_counter = p.ba_ctl + 2 + p.ba_rounds;
+        b.npairs = p.ba_ctl + 2 + 2 * p.ba_rounds;
+        b.bsum = p.bsum;
+        b.nscan = p.nscan;
+        const unsigned plan_blocks = (unsigned)std::min<uint64_t>((p.ba_cap[0] + 255) / 256, (uint64_t)ctx->sm_count * 16);
+        for (int r = 0; r < p.ba_rounds; ++r) {
+            b.round = (uint32_t)r;
+            b.off_cur = a.ba_off[r & 1];
+            b.off_next = a.ba_off[(r + 1) & 1];
+            b.in_pts = a.ba_pts[(r + 1) & 1];
+            b.in_inf = a.ba_inf[(r + 1) & 1];
+            b.out_pts = a.ba_pts[r & 1];
+            b.out_inf = a.ba_inf[r & 1];
+            k_ba_scan_local<<<p.nscan, SCAN_T, 0, st>>>(b);
+            k_ba_scan_bsum<<<1, SCAN_T, 0, st>>>(b);
+            k_ba_scan_add<<<p.nscan, SCAN_T, 0, st>>>(b);
+            if (r == 0) {
+                k_ba_plan<G, true><<<plan_blocks, 256, 0, st>>>(b);
+                k_batch_add<G, true><<<ctx->sm_count * BC::MINB, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
+            } else {
+                k_ba_plan<G, false><<<plan_blocks, 256, 0, st>>>(b);
+                k_batch_add<G, false><<<ctx->sm_count * BC::MINB, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
+            }
+            launches += 5;
+            ++acc_launches;
+        }
+        CU(cudaEventRecord(ln.ev[3], st));
+        k_bucket_reduce<G, true><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
+    } else {
+        CU(cudaMemsetAsync(a.group_counter, 0, 4, st));
+        CU(cudaMemsetAsync(a.edge_bucket, 0xff, (size_t)a.max_chunks * 2 * 4, st));
+        k_accumulate<G><<<ctx->sm_count * AC::MINB, AC::TS::THREADS, AC::TS::SMEM, st>>>(a);
+        launches += 1;
+        acc_launches = 1;
+        CU(cudaEventRecord(ln.ev[3], st));
         const uint32_t *in_pts = a.edges, *in_key = a.edge_bucket;
         uint32_t n_in = a.max_chunks;
         unsigned long long span = a.L;
@@ -169,8 +234,8 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
             n_in = n_out;
             flip ^= 1;
         } while (n_in > 1);
+        k_bucket_reduce<G, false><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
     }
-    k_bucket_reduce<G><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
     launches += 1;
     {
         const uint32_t *in = a.segsum;
@@ -201,11 +266,11 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     ln.info[0] = (uint64_t)c;
     ln.info[1] = (uint64_t)a.Wd;
     ln.info[2] = (uint64_t)n * a.Wd;
-    ln.info[3] = 1;
+    ln.info[3] = acc_launches;
     ln.info[4] = launches;
     ln.info[5] = (uint64_t)a.W;
     ln.info[6] = (uint64_t)cfg.NT;
-    ln.info[7] = 0;
+    ln.info[7] = (uint64_t)ctx->accumulator;
     return B200MSM_OK;
 }
 

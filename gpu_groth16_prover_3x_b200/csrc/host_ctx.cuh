@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -57,6 +58,7 @@ struct b200msm_ctx {
     int device = 0;
     int sm_count = 0;
     int c_override = 0;
+    int accumulator = 0;  // 0: batched-affine rounds (batch_affine.cuh), 1: Jacobian chains (k_accumulate)
     size_t table_budget = size_t(32) << 30;  // bytes of window tables per base set (0: never build tables)
     std::vector<BaseSet> sets;
     Lane lanes[NLANES];
@@ -122,6 +124,11 @@ struct Plan {
     size_t bytes;
     uint32_t *bsum;
     uint32_t nscan;
+    // batched-affine rounds
+    uint64_t ba_cap[2] = {0, 0};
+    int ba_rounds = 0;
+    uint4 *ba_pairs = nullptr;
+    uint32_t *ba_ctl = nullptr;
 };
 
 size_t align_up(size_t x, size_t al) { return (x + al - 1) / al * al; }

@@ -131,6 +131,33 @@ __global__ void __launch_bounds__(128) k_mb_fqmul(uint32_t *out, int iters) {
     if (s == 0x12345678u) out[0] = 1;
 }
 
+// latency of ONE field inversion executed by a single thread (the situation inside k_batch_add's tile_inverse):
+// a dependent chain of `iters` inversions on lane 0 of one warp.  MODE 0: fq_inv (fast path + fallback),
+// 1: plain binary gcd, 2: fast path only (out[1] counts failures of its final check).
+template <class M, int MODE>
+__global__ void __launch_bounds__(32) k_mb_inv(uint32_t *out, int iters) {
+    if (threadIdx.x != 0) return;
+    fq_t x, r;
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) x[i] = M::R2(i) ^ (0x01010101u * (uint32_t)i);
+    x[NLIMB - 1] &= 0xffffu;
+    uint32_t fails = 0;
+    for (int it = 0; it < iters; ++it) {
+        if (MODE == 0) fq_inv<M>(r, x);
+        else if (MODE == 1) { if (!fq_inv_plain<M>(r, x)) ++fails; }
+        else { if (!fq_inv_plain_fast<M>(r, x)) ++fails; }
+#pragma unroll
+        for (int i = 0; i < NLIMB; ++i) x[i] = r[i] ^ (uint32_t)(it + 1);
+        x[NLIMB - 1] &= 0xffffu;
+        x[0] |= 1u;
+    }
+    uint32_t s = 0;
+#pragma unroll
+    for (int i = 0; i < NLIMB; ++i) s ^= x[i];
+    out[0] = s;
+    out[1] = fails;
+}
+
 }  // namespace
 
 // ================================================================================================
@@ -284,6 +311,15 @@ int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream) {
     return B200MSM_OK;
 }
 
+int b200msm_set_accumulator(b200msm_ctx *ctx, int mode) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (mode != 0 && mode != 1) return fail(ctx, B200MSM_ERR_ARG, "accumulator mode %d (0: batched affine, 1: Jacobian chains)", mode);
+    for (int i = 0; i < NLANES; ++i)
+        if (ctx->lanes[i].pending) return fail(ctx, B200MSM_ERR_ARG, "lane %d still has an un-waited MSM", i);
+    ctx->accumulator = mode;
+    return B200MSM_OK;
+}
+
 int b200msm_set_table_budget(b200msm_ctx *ctx, size_t max_bytes_per_set) {
     if (!ctx) return B200MSM_ERR_ARG;
     ctx->table_budget = max_bytes_per_set;
@@ -320,7 +356,7 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
 
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     if (!ctx) return B200MSM_ERR_ARG;
-    if (!gops || iters <= 0 || kind < 0 || kind > 3) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    if (!gops || iters <= 0 || kind < 0 || kind > 6) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     uint32_t *d = nullptr;
     CU(cudaMalloc(&d, 256));
@@ -329,6 +365,26 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     CU(cudaEventCreate(&e1));
     const int blocks = ctx->sm_count * 8;
     double ops = 0;
+    if (kind >= 4) {  // single-thread inversion latency: returns microseconds per inversion
+        for (int rep = 0; rep < 2; ++rep) {
+            CU(cudaEventRecord(e0, 0));
+            if (kind == 4) k_mb_inv<ModA, 0><<<1, 32>>>(d, iters);
+            else if (kind == 5) k_mb_inv<ModA, 1><<<1, 32>>>(d, iters);
+            else k_mb_inv<ModA, 2><<<1, 32>>>(d, iters);
+            CU(cudaEventRecord(e1, 0));
+            CU(cudaEventSynchronize(e1));
+        }
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        uint32_t h[2] = {0, 0};
+        CU(cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost));
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFree(d);
+        if (kind == 6 && h[1]) return fail(ctx, B200MSM_ERR_CUDA, "fast inversion failed its final check %u times", h[1]);
+        *gops = double(ms) * 1e3 / iters;
+        return B200MSM_OK;
+    }
     for (int rep = 0; rep < 2; ++rep) {  // first repetition is the warm-up
         CU(cudaEventRecord(e0, 0));
         if (kind == 0) { k_mb_wide<<<blocks, 256>>>(d, iters); ops = double(blocks) * 256 * iters * MB_CHAINS; }

@@ -56,6 +56,12 @@ struct MsmArgs {
     uint32_t *winsum;           // W Jacobian points
     uint32_t *result;           // 1 Jacobian point
     uint32_t *group_counter;    // dynamic work counter for k_accumulate
+    // batched-affine accumulation (batch_affine.cuh): ping-pong round outputs; after the last executed round
+    // r = *ba_nrounds the bucket b holds at most one affine point, ba_pts[(r-1)&1][ba_off[r&1][b]]
+    uint32_t *ba_pts[2];
+    uint8_t *ba_inf[2];
+    uint32_t *ba_off[2];        // ba_off[0] == offs
+    uint32_t *ba_nrounds;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -415,11 +421,13 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_fold_edges(MsmArgs 
 }
 
 // running-sum reduction of one bucket segment per lane; out[w*nseg + seg] = sum_{j<m} (seg*m+j+1) * B[w][seg*m+j]
-template <class G>
+// AFF: buckets come from the batched-affine rounds (one affine point or nothing per bucket, mixed
+// additions); otherwise from the Jacobian bucket array written by k_accumulate / k_fold_edges.
+template <class G, bool AFF>
 __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_bucket_reduce(MsmArgs a) {
     typedef typename G::F F;
     typedef TailCfg<G> C;
-    constexpr int JACW = 3 * F::DEG * NLIMB;
+    constexpr int EW = F::DEG * NLIMB, AFFW = 2 * EW, JACW = 3 * EW;
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_flags[C::TPB][4];
     int team;
@@ -430,13 +438,30 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_bucket_reduce(MsmAr
     const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + lane;
     const bool valid = id < (uint32_t)a.W * a.nseg;
     const uint32_t w = valid ? id / a.nseg : 0u, seg = valid ? id % a.nseg : 0u;
+    const uint32_t *off = a.offs, *pts = nullptr;
+    const uint8_t *pinf = nullptr;
+    if (AFF) {
+        const uint32_t nr = *a.ba_nrounds;
+        off = a.ba_off[nr & 1u];
+        pts = a.ba_pts[(nr - 1u) & 1u];
+        pinf = a.ba_inf[(nr - 1u) & 1u];
+    }
     T.set_zero(tot.Z1);
     T.set_zero(run.Z1);
     bool run_inf = true;
     for (int j = (int)a.m - 1; j >= 0; --j) {
         const uint32_t key = w * a.NB + seg * a.m + (uint32_t)j;
-        const bool ne = valid && a.offs[key + 1] > a.offs[key];
-        if (team_any(ne)) {
+        const uint32_t o = valid ? off[key] : 0u;
+        bool ne = valid && off[key + 1] > o;
+        if (AFF) {
+            ne = ne && !pinf[o];
+            if (team_any(ne)) {
+                g2s(T, run.X2, pts + (size_t)o * AFFW, ne);
+                g2s(T, run.Y2, pts + (size_t)o * AFFW + EW, ne);
+                T.sync();
+                Ec<F>::madd(T, run, false, ne, run_inf);
+            }
+        } else if (team_any(ne)) {
             load_jac(T, run.X2, run.Y2, run.Z2, a.buckets + (size_t)key * JACW, ne);
             T.set_zero(run.Z2, !ne);
             Ec<F>::add(T, run, ne);

@@ -62,6 +62,7 @@ def load_library():
     lib.b200msm_set_stream.argtypes = [vp, ci, vp]
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
     lib.b200msm_set_table_budget.argtypes = [vp, sz]
+    lib.b200msm_set_accumulator.argtypes = [vp, ci]
     lib.b200msm_bases_info.argtypes = [vp, ci, _u64p]
     lib.b200msm_last_timings.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), _u64p]
     lib.b200msm_microbench.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double)]
@@ -245,8 +246,12 @@ class MsmContext:
         d = {k: float(ms[i]) for i, k in enumerate(self.PHASES)}
         d.update(window_bits=int(info[0]), windows=int(info[1]), entries=int(info[2]),
                  accumulate_launches=int(info[3]), kernel_launches=int(info[4]), bucket_sets=int(info[5]),
-                 tables=int(info[6]))
+                 tables=int(info[6]), accumulator=int(info[7]))
         return d
+
+    def set_accumulator(self, mode):
+        """0: batched-affine rounds (default), 1: Jacobian mixed-addition chains."""
+        self._check(self.lib.b200msm_set_accumulator(self._h, mode))
 
     def set_table_budget(self, max_bytes_per_set):
         """Byte budget of the window tables built at upload time (0: none), see include/b200_msm.h."""

@@ -101,6 +101,10 @@ int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size
 int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream);
 
 /* Tuning / introspection. */
+/* Bucket accumulation algorithm: 0 (default) = rounds of pairwise AFFINE additions sharing one field
+ * inversion per tile (6 field multiplications per addition), 1 = per-lane Jacobian mixed-addition chains
+ * (11 per addition; the round-1 baseline, kept for A/B measurement).  Results are identical. */
+int b200msm_set_accumulator(b200msm_ctx *ctx, int mode);
 /* Window width for MSMs and for the tables of base sets uploaded afterwards; 0 = automatic.  An MSM
  * whose forced width differs from the one its base set's tables were built for ignores the tables. */
 int b200msm_set_window_bits(b200msm_ctx *ctx, int c);
@@ -108,8 +112,8 @@ int b200msm_set_window_bits(b200msm_ctx *ctx, int c);
  * CUDA events on the launching stream: [0] total, [1] H2D scalars, [2] recode+sort,
  * [3] bucket accumulation (k_accumulate), [4] bucket reduction + window combine, [5] D2H result.
  * info[0] = window bits c, [1] = signed digits (windows) per scalar, [2] = sorted entries,
- * [3] = k_accumulate launches (1), [4] = total kernel launches of the MSM, [5] = bucket sets G,
- * [6] = window tables used NT, [7] = reserved. */
+ * [3] = accumulation launches (batched-affine rounds enqueued, or 1), [4] = total kernel launches of the
+ * MSM, [5] = bucket sets G, [6] = window tables used NT, [7] = accumulator mode. */
 int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[8]);
 
 /* Synthetic microbenchmarks used by bench.py for the roofline denominator: runs `iters`
@@ -119,7 +123,10 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
  *           on B200: 32 per clock per SM), 1 = IMAD (mad.lo, 64 per clock per SM),
  *       2 = the engine's own Fq Montgomery multiplication (32-bit CIOS on IMAD.WIDE.U32.X carry
  *           chains; returns 10^9 modmul/s),
- *       3 = the reduced-radix (29-bit limbs, carry-free IMAD.WIDE.U32) experiment, for comparison. */
+ *       3 = the reduced-radix (29-bit limbs, carry-free IMAD.WIDE.U32) experiment, for comparison;
+ *       4, 5, 6 = latency of one Fq inversion by a single thread, in MICROSECONDS (not a rate): the engine's
+ *           fq_inv, the plain binary gcd, the approximation-based fast path alone (fails if it ever needs
+ *           the fallback). */
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops);
 
 /* Self-test hooks (used by tests/ only): the device field / point layer applied elementwise.

@@ -54,7 +54,7 @@ def emu():
     d = os.path.join(ROOT, "tests", "host_emu")
     so = os.path.join(d, "libemu.so")
     srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f)
-                                            for f in ("prim.cuh", "fq.cuh", "fe.cuh", "ec.cuh", "curves.cuh")]
+                                            for f in ("prim.cuh", "fq.cuh", "fe.cuh", "ec.cuh", "curves.cuh", "batch_affine.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU", "-x", "c++",
                         srcs[0], "-o", so], check=True)
@@ -63,6 +63,9 @@ def emu():
     lib.emu_field_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, u64p]
     lib.emu_point_op.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p, u64p, ctypes.c_int, u64p]
     lib.emu_fq_mul.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, u64p]
+    lib.emu_affine_add.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, ctypes.c_int, u64p]
+    lib.emu_field_inv.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
+    lib.emu_fq_inv.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
     lib.emu_fr_from_mont.argtypes = [ctypes.c_int, ctypes.c_size_t, u64p, u64p]
     return lib
 

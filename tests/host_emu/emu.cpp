@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "../../gpu_groth16_prover_3x_b200/csrc/curves.cuh"
+#include "../../gpu_groth16_prover_3x_b200/csrc/batch_affine.cuh"
 
 using namespace mnt753;
 
@@ -93,9 +94,57 @@ int point_op(int op, const uint64_t *acc, const uint64_t *q, int flags, uint64_t
     return ret;
 }
 
+// one batched-affine addition with a batch of one: forward, inversion of the lone denominator, backward.
+// has2 = 0: copy of p1.  Returns 1 when the result is infinity.
+template <class G>
+int affine_add(const uint64_t *p1, const uint64_t *p2, int has2, uint64_t *out) {
+    typedef typename G::F F;
+    Emu<G> E;
+    const size_t st = 12 * Emu<G>::DEG;
+    const BaSlots s = {0, 1, 2, 3, 4, 5, 6, 7};
+    E.put(s.X1, p1); E.put(s.Y1, p1 + st);
+    if (has2) { E.put(s.X2, p2); E.put(s.Y2, p2 + st); }
+    E.T.set_one(s.INV);
+    const uint32_t code = pair_forward(E.T, s, true, has2 != 0, [](bool) {});
+    E.T.copy(s.PRE, s.INV);                 // exclusive prefix of a batch of one
+    E.T.mul(s.INV, s.INV, s.D);
+    tile_inverse(E.T, s.INV, 8, 9, 10, 11);
+    E.put(s.X1, p1); E.put(s.Y1, p1 + st);
+    if (has2) { E.put(s.X2, p2); E.put(s.Y2, p2 + st); }
+    const bool inf = pair_backward(E.T, s, code, false);
+    E.get(s.X2, out); E.get(s.Y2, out + st);
+    return inf ? 1 : 0;
+}
+
+template <class G>
+int field_inv(size_t n, const uint64_t *a, uint64_t *out) {
+    Emu<G> E;
+    const size_t st = 12 * Emu<G>::DEG;
+    for (size_t i = 0; i < n; ++i) {
+        E.put(0, a + i * st);
+        E.T.inv_lane0(1, 0, 2, 3);
+        E.get(1, out + i * st);
+    }
+    return 0;
+}
+
 }  // namespace
 
 extern "C" {
+int emu_affine_add(int curve, int group, const uint64_t *p1, const uint64_t *p2, int has2, uint64_t *out) {
+    if (curve == 0 && group == 1) return affine_add<Mnt4G1>(p1, p2, has2, out);
+    if (curve == 0 && group == 2) return affine_add<Mnt4G2>(p1, p2, has2, out);
+    if (curve == 1 && group == 1) return affine_add<Mnt6G1>(p1, p2, has2, out);
+    if (curve == 1 && group == 2) return affine_add<Mnt6G2>(p1, p2, has2, out);
+    return -1;
+}
+int emu_field_inv(int curve, int group, size_t n, const uint64_t *a, uint64_t *out) {
+    if (curve == 0 && group == 1) return field_inv<Mnt4G1>(n, a, out);
+    if (curve == 0 && group == 2) return field_inv<Mnt4G2>(n, a, out);
+    if (curve == 1 && group == 1) return field_inv<Mnt6G1>(n, a, out);
+    if (curve == 1 && group == 2) return field_inv<Mnt6G2>(n, a, out);
+    return -1;
+}
 int emu_field_op(int curve, int group, int op, size_t n, const uint64_t *a, const uint64_t *b, uint64_t *out) {
     if (curve == 0 && group == 1) return field_op<Mnt4G1>(op, n, a, b, out);
     if (curve == 0 && group == 2) return field_op<Mnt4G2>(op, n, a, b, out);
@@ -122,6 +171,33 @@ int emu_fq_mul(int modulus, int which, size_t n, const uint64_t *a, const uint64
         memcpy(out + 12 * i, r, 96);
     }
     return 0;
+}
+// which: 0 = fq_inv (fast path with fallback), 1 = plain binary gcd only, 2 = fast path only (returns the
+// number of inputs on which the fast path reported failure); the plain-integer variants are wrapped the same
+// way as fq_inv so that all three return the Montgomery-form inverse
+int emu_fq_inv(int modulus, int which, size_t n, const uint64_t *a, uint64_t *out) {
+    int failed = 0;
+    for (size_t i = 0; i < n; ++i) {
+        fq_t x, r, t, r2;
+        memcpy(x, a + 12 * i, 96);
+        if (which == 0) {
+            if (modulus == 0) fq_inv<ModA>(r, x); else fq_inv<ModB>(r, x);
+        } else {
+            bool ok;
+            if (modulus == 0) {
+                ok = which == 1 ? fq_inv_plain<ModA>(t, x) : fq_inv_plain_fast<ModA>(t, x);
+                for (int k = 0; k < NLIMB; ++k) r2[k] = ModA::R2(k);
+                fq_mul<ModA>(t, t, r2); fq_mul<ModA>(r, t, r2);
+            } else {
+                ok = which == 1 ? fq_inv_plain<ModB>(t, x) : fq_inv_plain_fast<ModB>(t, x);
+                for (int k = 0; k < NLIMB; ++k) r2[k] = ModB::R2(k);
+                fq_mul<ModB>(t, t, r2); fq_mul<ModB>(r, t, r2);
+            }
+            if (!ok) ++failed;
+        }
+        memcpy(out + 12 * i, r, 96);
+    }
+    return failed;
 }
 int emu_fr_from_mont(int curve, size_t n, const uint64_t *in, uint64_t *out) {
     for (size_t i = 0; i < n; ++i) {

@@ -132,6 +132,29 @@ def test_window_tables(ctxs, oracle, golden, curve, group):
         ctx.set_table_budget(32 << 30)
 
 
+@pytest.mark.parametrize("curve,group", CG)
+def test_jacobian_chain_accumulator(ctxs, oracle, golden, curve, group):
+    """The round-1 baseline accumulator (per-lane Jacobian mixed-addition chains + edge fold) stays
+    selectable for A/B measurement and must give the same points as the batched-affine rounds."""
+    z = golden["msm_vectors"]
+    key = "c%d_g%d" % (curve, group)
+    bases, sc = z[key + "_bases"], z[key + "_scalars"]
+    ctx = ctxs[curve]
+    slot = ctx.upload_bases(group, bases)
+    try:
+        ctx.set_accumulator(1)
+        for c in (0, 6, 13):
+            ctx.set_window_bits(c)
+            for n in (257, 33, 1):
+                got = affine(oracle, curve, group, ctx.msm(slot, sc[:n * 12], n))
+                assert (got == z["%s_n%d_out" % (key, n)]).all(), (c, n)
+                assert ctx.last_timings()["accumulator"] == 1
+    finally:
+        ctx.set_accumulator(0)
+        ctx.set_window_bits(0)
+        ctx.free_bases(slot)
+
+
 def test_async_lanes_and_shards(ctxs, oracle):
     """Four MSMs in flight on four lanes (A, B1, L on G1; B2 on G2), then the point-range sharding
     identity: the fold of per-shard partials equals the unsharded MSM."""

@@ -143,3 +143,76 @@ def test_emu_both_multipliers(emu, oracle, golden, modulus):
         out = np.zeros_like(a)
         emu.emu_fq_mul(modulus, which, a.size // 12, _p(a), _p(b), _p(out))
         assert (out == want).all(), which
+
+
+@pytest.mark.parametrize("modulus", [0, 1])
+def test_emu_fq_inverse(emu, oracle, golden, modulus):
+    """Binary extended-Euclid inversion (fq.cuh fq_inv, used by the batched-affine accumulation) against
+    the oracle's field inversion: edge values (0 -> 0, 1, 2, p-1, powers of two) and random operands."""
+    z = golden["field_vectors"]
+    key = "c%d_f0" % modulus
+    rng = np.random.default_rng(11 + modulus)
+    p = po.fq_modulus(modulus)
+    edge = [0, 1, 2, 3, p - 1, p - 2, (p + 1) // 2, 1 << 752, (1 << 700) % p, po.R % p, po.R * po.R % p, 1 << 31, 1 << 32, (1 << 64) - 1]
+    small = [pow(2, k, p) for k in range(0, 760, 37)] + [(p - pow(2, k, p)) % p for k in range(1, 760, 41)] + list(range(1, 40))
+    a = np.concatenate([z[key + "_a"], po.ints_to_array(edge + small + [int.from_bytes(rng.bytes(100), "little") % p for _ in range(1500)])])
+    want = oracle.field_op(modulus, 0, 4, a)
+    nz = int(np.count_nonzero(a.reshape(-1, 12).any(axis=1) == 0))
+    for which in (0, 1, 2):
+        out = np.zeros_like(a)
+        failed = emu.emu_fq_inv(modulus, which, a.size // 12, _p(a), _p(out))
+        assert (out == want).all(), which
+        assert failed == (nz if which else 0), which      # the fast path itself never needs the fallback (except for 0)
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_emu_tower_inverse(emu, oracle, golden, curve, group):
+    """Team::inv_lane0: Fq by binary gcd, Fq2 / Fq3 through the norm (conjugate / Frobenius images)."""
+    z = golden["field_vectors"]
+    f = 0 if group == 1 else 1
+    a = z["c%d_f%d_a" % (curve, f)]
+    deg = po.degree(curve, group)
+    a = a.reshape(-1, 12 * deg)
+    a = a[a.any(axis=1)].reshape(-1)          # inverse of zero is never requested
+    out = np.zeros_like(a)
+    assert emu.emu_field_inv(curve, group, a.size // (12 * deg), _p(a), _p(out)) == 0
+    assert (out == oracle.field_op(curve, f, 4, a)).all()
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_emu_batched_affine_pair(emu, oracle, golden, curve, group):
+    """pair_forward / tile_inverse / pair_backward (batch_affine.cuh) on single pairs: generic sums from
+    the golden vectors, P + P (doubling through lambda = (3x^2 + a) / 2y), P + (-P) -> infinity, copy."""
+    z = golden["point_vectors"]
+    key = "c%d_g%d" % (curve, group)
+    deg = po.degree(curve, group)
+    w = 24 * deg
+    A, B = z[key + "_a"].reshape(-1, w), z[key + "_b"].reshape(-1, w)
+    add_out = z[key + "_add_out"].reshape(-1, w)
+
+    def run(p1, p2, has2=1):
+        out = np.zeros(w, np.uint64)
+        inf = emu.emu_affine_add(curve, group, _p(p1), _p(p2 if p2 is not None else p1), has2, _p(out))
+        return out, inf
+
+    n = 0
+    for i in range(A.shape[0]):
+        if not A[i][12 * deg:].any() or not B[i][12 * deg:].any():
+            continue                           # infinities are resolved by the plan kernel, never fed to a pair
+        out, inf = run(A[i], B[i])
+        if add_out[i].any():
+            assert inf == 0 and (out == add_out[i]).all(), i
+        else:
+            assert inf == 1 and not out.any(), i
+        n += 1
+    assert n >= 4
+    pts = oracle.gen_bases(curve, group, 6).reshape(6, w)
+    for p in pts[:3]:
+        out, inf = run(p, p)
+        assert inf == 0 and (out == oracle.point_op(curve, group, 1, p)).all()
+        out, inf = run(p, oracle.point_op(curve, group, 4, p))
+        assert inf == 1 and not out.any()
+        out, inf = run(p, None, has2=0)
+        assert inf == 0 and (out == p).all()
+    out, inf = run(pts[3], pts[4])
+    assert (out == oracle.point_op(curve, group, 0, pts[3], pts[4])).all()
