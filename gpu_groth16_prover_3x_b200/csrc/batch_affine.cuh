@@ -34,63 +34,65 @@ constexpr uint32_t BA_NONE = 0xffffffffu;
 constexpr int BA_BMAX = 64;  // additions per lane and tile
 enum : uint32_t { BA_NORMAL = 0, BA_DBL = 1, BA_CANCEL = 2, BA_COPY1 = 3, BA_IDLE = 4 };
 
-struct BaSlots { int X1, Y1, X2, Y2, INV, PRE, D, T; };
+// Six slab slots per team: the operands, the running inverse and one prefix/scratch.  The denominator
+// overwrites X2 (x2 is recovered as x1 + d), lambda overwrites Y2.
+struct BaSlots { int X1, Y1, X2, Y2, INV, PRE; };
 
-// Phase 1 of one addition: slots X1, X2 hold the abscissae (X2 only where has2).  Computes the
-// denominator D and classifies the pair.  load_y(pred) must bring (signed) Y1, Y2 into their slots for
-// the lanes with pred; it is called only when some lane has x1 == x2.
+// Phase 1 of one addition: slots X1, X2 hold the abscissae (X2 only where has2).  Leaves the denominator
+// d in X2 and classifies the pair.  load_y(pred) must bring (signed) Y1, Y2 into their slots for the
+// lanes with pred; it is called only when some lane has x1 == x2.  PRE is scratch.
 template <class F, class LoadY>
 MSM_DEVICE uint32_t pair_forward(const Team<F> &T, const BaSlots &s, bool valid, bool has2, LoadY load_y) {
-    T.sub(s.D, s.X2, s.X1);
-    const bool dz = T.is_zero(s.D);
+    T.sub(s.X2, s.X2, s.X1);
+    const bool dz = T.is_zero(s.X2);
     const bool need_y = has2 && dz;
     uint32_t code = !valid ? BA_IDLE : (!has2 ? BA_COPY1 : BA_NORMAL);
     if (team_any(need_y)) {
         load_y(need_y);
-        T.sub(s.T, s.Y2, s.Y1);
-        const bool eq = T.is_zero(s.T);
+        T.sub(s.PRE, s.Y2, s.Y1);
+        const bool eq = T.is_zero(s.PRE);
         const bool y0 = T.is_zero(s.Y1);   // a point of order two doubles to infinity
         const bool dbl = need_y && eq && !y0;
         if (need_y) code = dbl ? BA_DBL : BA_CANCEL;
-        T.dbl(s.D, s.Y1, dbl);
+        T.dbl(s.X2, s.Y1, dbl);
     }
-    T.set_one(s.D, code >= BA_CANCEL);
+    T.set_one(s.X2, code >= BA_CANCEL);
     return code;
 }
 
 // Phase 2: slots X1, Y1, X2, Y2 hold the (signed) operands, PRE the prefix product, INV the running
 // inverse.  Leaves the sum in (X2, Y2) and advances INV.  Returns true when the result is infinity.
 template <class F>
-MSM_DEVICE bool pair_backward(const Team<F> &T, const BaSlots &s, uint32_t code, bool a_inf) {
+MSM_DEVICE bool pair_backward(const Team<F> &T, const BaSlots &s, uint32_t code) {
     const bool dbl = code == BA_DBL;
     const bool any_dbl = team_any(dbl);
-    T.sub(s.D, s.X2, s.X1);
-    if (any_dbl) T.dbl(s.D, s.Y1, dbl);
-    T.set_one(s.D, code >= BA_CANCEL);
+    T.sub(s.X2, s.X2, s.X1);             // d = x2 - x1
+    if (any_dbl) T.dbl(s.X2, s.Y1, dbl); //   or 2 y1
+    T.set_one(s.X2, code >= BA_CANCEL);
     T.mul(s.PRE, s.INV, s.PRE);          // 1 / d
-    T.mul(s.INV, s.INV, s.D);            // inverse of the shorter prefix
-    T.sub(s.Y2, s.Y2, s.Y1);             // numerator
-    if (any_dbl) {                       // 3 x1^2 + a
-        T.sqr(s.T, s.X1);
-        T.dbl(s.D, s.T);
-        T.add(s.T, s.T, s.D);
-        T.set_one(s.D);
-        T.mul_by_a(s.D, s.D);
-        T.add(s.Y2, s.T, s.D, dbl);
+    T.mul(s.INV, s.INV, s.X2);           // inverse of the shorter prefix
+    T.sub(s.Y2, s.Y2, s.Y1);             // numerator y2 - y1
+    if (any_dbl) {                       //   or 3 x1^2 + a; d is dead on those lanes, X2 <- 0 so that x1 + x2 = 2 x1 below
+        T.sqr(s.X2, s.X1, dbl);
+        T.add(s.Y2, s.X2, s.X2, dbl);
+        T.add(s.Y2, s.Y2, s.X2, dbl);
+        T.set_one(s.X2, dbl);
+        T.mul_by_a(s.X2, s.X2, dbl);
+        T.add(s.Y2, s.Y2, s.X2, dbl);
+        T.set_zero(s.X2, dbl);
     }
-    T.mul(s.D, s.Y2, s.PRE);             // lambda
-    T.add(s.X2, s.X1, s.X2);
-    T.sqr(s.PRE, s.D);
+    T.mul(s.Y2, s.Y2, s.PRE);            // lambda
+    T.sqr(s.PRE, s.Y2);
+    T.add(s.X2, s.X2, s.X1);
+    T.add(s.X2, s.X2, s.X1);             // x1 + x2 = 2 x1 + d
     T.sub(s.X2, s.PRE, s.X2);            // x3 = lambda^2 - x1 - x2
     T.sub(s.PRE, s.X1, s.X2);
-    T.mul(s.PRE, s.D, s.PRE);
+    T.mul(s.PRE, s.Y2, s.PRE);
     T.sub(s.Y2, s.PRE, s.Y1);            // y3 = lambda (x1 - x3) - y1
     const bool copy1 = code == BA_COPY1, cancel = code == BA_CANCEL;
-    T.copy(s.X2, s.X1, copy1);
-    T.copy(s.Y2, s.Y1, copy1);
-    T.set_zero(s.X2, cancel);
-    T.set_zero(s.Y2, cancel);
-    return cancel || (copy1 && a_inf);
+    if (team_any(copy1)) { T.copy(s.X2, s.X1, copy1); T.copy(s.Y2, s.Y1, copy1); }
+    if (team_any(cancel)) { T.set_zero(s.X2, cancel); T.set_zero(s.Y2, cancel); }
+    return cancel;
 }
 
 // After the forward pass INV holds each lane's product of denominators.  Replace it by the lane's own
@@ -270,9 +272,9 @@ __global__ void __launch_bounds__(256) k_ba_plan(BaArgs a) {
 template <class G>
 struct BaCfg {
     static constexpr int DEG = G::F::DEG;
-    static constexpr int NSLOT = 8;
-    static constexpr int TPB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 1);
-    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 3);
+    static constexpr int NSLOT = 6;   // 18 KB of slab per warp: 12 warps per SM
+    static constexpr int TPB = DEG == 1 ? 4 : (DEG == 2 ? 2 : 1);
+    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 3 : 4);
     typedef TeamSetup<G, NSLOT, TPB> TS;
 };
 
@@ -298,26 +300,38 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
     int team;
     const Team<F> T = C::TS::make(smem, s_flags, team);
     const int lane = threadIdx.x & 31;
-    const BaSlots s = {0, 1, 2, 3, 4, 5, 6, 7};
+    const BaSlots s = {0, 1, 2, 3, 4, 5};
     const uint32_t *in = FIRST ? a.bases : a.in_pts;
 
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.nrounds = a.round + 1;
     const uint32_t E = a.npairs[a.round];
-    // additions per lane and tile: enough tiles to give every resident team a few
+    // Tile = 32 lanes x B consecutive pairs of the list, claimed from an atomic cursor.  Small rounds: one
+    // tile per team (a round then costs one inversion latency, not several).  Large rounds: full tiles of
+    // BA_BMAX while more than one full tile per team is left, then the remainder in equal shares, so that
+    // the teams finish together without paying for many small tiles (each tile costs one inversion).
     const uint32_t teams = gridDim.x * C::TPB;
-    uint32_t B = (E + teams * 32u * 3u - 1u) / (teams * 32u * 3u);
-    B = B < 1u ? 1u : (B > (uint32_t)BA_BMAX ? (uint32_t)BA_BMAX : B);
-    const uint32_t per_tile = 32u * B;
-    const uint32_t ntiles = (E + per_tile - 1u) / per_tile;
+    const uint32_t B0 = (E + teams * 32u - 1u) / (teams * 32u);
     const uint4 idle = make_uint4(0u, 0u, 0u, 0u);
+    __shared__ uint32_t s_B[C::TPB];
 
     for (;;) {
         T.sync();
-        if (T.comp == 0 && lane == 0) s_tile[team] = atomicAdd(a.tile_counter + a.round, 1u);
+        if (T.comp == 0 && lane == 0) {
+            uint32_t Bt;
+            if (B0 <= (uint32_t)BA_BMAX) Bt = B0 < 1u ? 1u : B0;
+            else {
+                const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(a.tile_counter + a.round);
+                const uint32_t rem = E > cur ? E - cur : 0u;
+                Bt = (rem + teams * 32u - 1u) / (teams * 32u);
+                Bt = Bt < 16u ? 16u : (Bt > (uint32_t)BA_BMAX ? (uint32_t)BA_BMAX : Bt);
+            }
+            s_tile[team] = atomicAdd(a.tile_counter + a.round, 32u * Bt);
+            s_B[team] = Bt;
+        }
         T.sync();
-        const uint32_t tile = s_tile[team];
-        if (tile >= ntiles) break;
-        const uint32_t base = tile * per_tile;
+        const uint32_t base = s_tile[team];
+        const uint32_t B = s_B[team];
+        if (base >= E) break;
 
         // ---- forward: denominators and prefix products
         T.set_one(s.INV);
@@ -344,7 +358,7 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
             });
             if (valid && T.comp == 0) a.out_inf[j] = (uint8_t)code;   // parked until the backward pass
             s2g(T, a.out_pts + (size_t)j * AFFW, s.INV, valid);       // exclusive prefix, parked in the output slot
-            T.mul(s.INV, s.INV, s.D);
+            T.mul(s.INV, s.INV, s.X2);
         }
         // ---- one inversion for the whole tile
         tile_inverse(T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
@@ -375,7 +389,7 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
             g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
             g2s(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
             if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, valid); T.neg_if(s.Y2, s.Y2, d.y >> 31, valid); }
-            const bool res_inf = pair_backward(T, s, code, false);
+            const bool res_inf = pair_backward(T, s, code);
             s2g(T, a.out_pts + (size_t)j * AFFW, s.X2, valid);
             s2g(T, a.out_pts + (size_t)j * AFFW + EW, s.Y2, valid);
             if (valid && T.comp == 0) a.out_inf[j] = res_inf ? 1 : 0;

@@ -30,8 +30,11 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     a.L = (uint32_t)L;
     a.max_chunks = (uint32_t)((emax + L - 1) / L) + 1;
     // bucket-reduce segment length: keep >= ~32k lanes of segments when there are that many buckets
+    // (one wave of k_bucket_reduce: its 12-slot teams fit 6 per SM for G1, fewer for the towers)
+    typedef TailCfg<G> TCp;
+    const uint64_t resident_lanes = (uint64_t)ctx->sm_count * std::max<size_t>(1, (size_t)(220 * 1024) / (TCp::TS::SMEM + 1024)) * TCp::TPB * 32;
     uint32_t m = 1;
-    while ((uint64_t)a.K / (m * 2) >= 32768 && m * 2 <= a.NB && m < 64) m *= 2;
+    while ((uint64_t)a.K / m > resident_lanes && m * 2 <= a.NB && m < 256) m *= 2;
     a.m = m;
     a.nseg = a.NB / m;
     p.nscan = (a.K + SCAN_B - 1) / SCAN_B;
@@ -245,7 +248,7 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
         while (nin > 1) {
             const uint32_t nout = (nin + 31) / 32;
             uint32_t *out = nout == 1 ? a.winsum : bufs[flip];
-            k_sum<G><<<((unsigned)a.W * nout + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(
+            k_sum<G><<<((unsigned)a.W * nout + TC::TPB - 1) / TC::TPB, TC::TS::THREADS, TC::TS::SMEM, st>>>(
                 in, out, (uint32_t)a.W, nin, 32u);
             ++launches;
             in = out;
@@ -385,7 +388,7 @@ int run_fold(b200msm_ctx *ctx, const uint64_t *xyz, size_t n, uint64_t *out) {
     int flip = 0;
     do {  // at least one pass so that the input is never aliased
         const uint32_t nout = (nin + 31) / 32;
-        k_sum<G><<<(nout + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM>>>(in, buf[flip], 1u, nin, 32u);
+        k_sum<G><<<(nout + TC::TPB - 1) / TC::TPB, TC::TS::THREADS, TC::TS::SMEM>>>(in, buf[flip], 1u, nin, 32u);
         in = buf[flip];
         nin = nout;
         flip ^= 1;

@@ -101,17 +101,17 @@ int affine_add(const uint64_t *p1, const uint64_t *p2, int has2, uint64_t *out) 
     typedef typename G::F F;
     Emu<G> E;
     const size_t st = 12 * Emu<G>::DEG;
-    const BaSlots s = {0, 1, 2, 3, 4, 5, 6, 7};
+    const BaSlots s = {0, 1, 2, 3, 4, 5};
     E.put(s.X1, p1); E.put(s.Y1, p1 + st);
     if (has2) { E.put(s.X2, p2); E.put(s.Y2, p2 + st); }
     E.T.set_one(s.INV);
     const uint32_t code = pair_forward(E.T, s, true, has2 != 0, [](bool) {});
     E.T.copy(s.PRE, s.INV);                 // exclusive prefix of a batch of one
-    E.T.mul(s.INV, s.INV, s.D);
+    E.T.mul(s.INV, s.INV, s.X2);
     tile_inverse(E.T, s.INV, 8, 9, 10, 11);
     E.put(s.X1, p1); E.put(s.Y1, p1 + st);
     if (has2) { E.put(s.X2, p2); E.put(s.Y2, p2 + st); }
-    const bool inf = pair_backward(E.T, s, code, false);
+    const bool inf = pair_backward(E.T, s, code);
     E.get(s.X2, out); E.get(s.Y2, out + st);
     return inf ? 1 : 0;
 }
