@@ -34,8 +34,14 @@ def up_to_date():
     return all(os.path.getmtime(s) <= t for s in sources())
 
 
-def build(force=False, verbose=False):
-    """Build the CUDA library in-tree; returns its path."""
+def build(force=False, verbose=False, extra_flags=None, out=None):
+    """Build the CUDA library in-tree; returns its path.  extra_flags / out build a VARIANT of the same
+    library next to it (development A/B runs: e.g. extra_flags=["-DMNT753_MUL_ROLL=8"])."""
+    global LIB, OBJ
+    if extra_flags or out:
+        LIB = out or LIB
+        OBJ = OBJ + "_variant"
+        force = True
     if not force and up_to_date():
         return LIB
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
@@ -43,7 +49,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found: cannot build libb200msm.so")
     os.makedirs(OBJ, exist_ok=True)
     ccbin = ["-ccbin", HOST_CXX] if os.path.exists(HOST_CXX) else []
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + list(extra_flags or [])
 
     def compile_one(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
@@ -65,4 +71,6 @@ def build(force=False, verbose=False):
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a[len("--out="):] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=defs, out=outs[0] if outs else None))

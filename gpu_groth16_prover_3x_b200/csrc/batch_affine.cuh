@@ -31,7 +31,7 @@
 namespace mnt753 {
 
 constexpr uint32_t BA_NONE = 0xffffffffu;
-constexpr int BA_BMAX = 64;  // additions per lane and tile
+constexpr int BA_BMAX = 256;  // additions per lane and tile
 enum : uint32_t { BA_NORMAL = 0, BA_DBL = 1, BA_CANCEL = 2, BA_COPY1 = 3, BA_IDLE = 4 };
 
 // Six slab slots per team: the operands, the running inverse and one prefix/scratch.  The denominator
@@ -335,20 +335,21 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
 
         // ---- forward: denominators and prefix products
         T.set_one(s.INV);
+        // descriptors are read two steps ahead and the coordinates of the next step are pulled into L2, so
+        // that neither the list nor the gathers are waited for at DRAM latency
         uint4 nxt = (base + lane < E) ? a.pairs[base + lane] : idle;
+        uint4 nxt2 = (B > 1u && base + 32u + lane < E) ? a.pairs[base + 32u + lane] : idle;
         for (uint32_t i = 0; i < B; ++i) {
             const uint32_t p = base + i * 32u + lane;
             const bool valid = p < E;
             const uint4 d = nxt;
             const uint32_t r1 = d.x & 0x7fffffffu, r2 = d.y & 0x7fffffffu, j = d.z;
-            if (i + 1 < B) {   // next step's sources: descriptor now, coordinates into L2
-                const uint32_t pn = p + 32u;
-                nxt = (pn < E) ? a.pairs[pn] : idle;
-                if (pn < E) {
-                    prefetch_coord(T, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW);
-                    prefetch_coord(T, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW);
-                }
+            nxt = nxt2;
+            if (i + 1 < B && p + 32u < E) {
+                prefetch_coord(T, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW);
+                prefetch_coord(T, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW);
             }
+            nxt2 = (i + 2 < B && p + 64u < E) ? a.pairs[p + 64u] : idle;
             g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
             g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
             const uint32_t code = pair_forward(T, s, valid, valid, [&](bool pred) {
@@ -366,22 +367,22 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
         {
             const uint32_t pl = base + (B - 1u) * 32u + lane;
             nxt = (pl < E) ? a.pairs[pl] : idle;
+            nxt2 = (B > 1u && pl - 32u < E) ? a.pairs[pl - 32u] : idle;
         }
         for (int i = (int)B - 1; i >= 0; --i) {
             const uint32_t p = base + (uint32_t)i * 32u + lane;
             const bool valid = p < E;
             const uint4 d = nxt;
             const uint32_t r1 = d.x & 0x7fffffffu, r2 = d.y & 0x7fffffffu, j = d.z;
-            if (i > 0) {
-                const uint32_t pn = p - 32u;     // pn < p; valid whenever any later index of the lane is
-                nxt = (pn < E) ? a.pairs[pn] : idle;
-                if (pn < E) {
-                    const uint32_t *n1 = in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, *n2 = in + (size_t)(nxt.y & 0x7fffffffu) * AFFW;
-                    prefetch_coord(T, n1); prefetch_coord(T, n1 + EW);
-                    prefetch_coord(T, n2); prefetch_coord(T, n2 + EW);
-                    prefetch_coord(T, a.out_pts + (size_t)nxt.z * AFFW);
-                }
+            nxt = nxt2;
+            if (i > 0 && p - 32u < E) {
+                const uint32_t *n1 = in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, *n2 = in + (size_t)(nxt.y & 0x7fffffffu) * AFFW;
+                prefetch_coord(T, n1); prefetch_coord(T, n1 + EW);
+                prefetch_coord(T, n2); prefetch_coord(T, n2 + EW);
+                prefetch_coord(T, a.out_pts + (size_t)nxt.z * AFFW);
+                prefetch_l2(a.out_inf + nxt.z);
             }
+            nxt2 = (i > 1 && p - 64u < E) ? a.pairs[p - 64u] : idle;
             const uint32_t code = valid ? a.out_inf[j] : (uint32_t)BA_IDLE;
             g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
             g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);

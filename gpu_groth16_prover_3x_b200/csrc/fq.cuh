@@ -237,6 +237,99 @@ MSM_DEVICE void fq_dot(fq_t &r, const uint32_t (&a)[K][NLIMB], BSrc &bsrc) {
     fq_cond_sub<M>(r, t);
 }
 
+
+// ---- the same dot product with the row loop kept ROLLED in blocks of RU rows ----------------------------
+// The fully unrolled fq_dot is ~1.4k instructions (22 KB) of straight-line code; with three warps per
+// scheduler at different places in it the instruction fetch cannot keep up (measured: the slab multiplier
+// reaches 97 % of the IMAD.WIDE pipe with 8 warps per SM but only 86 % with 12).  Here a block of RU rows
+// is unrolled (the per-row ">> 32" stays register renaming inside the block) and the block is iterated
+// 24 / RU times; the loop-carried accumulators cost one register move each per block.
+// b must come from memory (BQuads): a register-resident b cannot be indexed by the loop counter.
+template <class M, int K, int RU, class BSrc>
+MSM_DEVICE void fq_dot_rolled(fq_t &r, const uint32_t (&a)[K][NLIMB], BSrc &bsrc) {
+    static_assert(RU % 4 == 0 && NLIMB % RU == 0, "rows per block: a multiple of 4 dividing 24");
+    uint32_t E[NLIMB + 1], O[NLIMB];
+#pragma unroll
+    for (int j = 0; j <= NLIMB; ++j) E[j] = 0;
+#pragma unroll
+    for (int j = 0; j < NLIMB; ++j) O[j] = 0;
+#pragma unroll 1
+    for (int blk = 0; blk < NLIMB / RU; ++blk) {
+        uint4 bq[K];
+#pragma unroll
+        for (int rr = 0; rr < RU; ++rr) {
+            if ((rr & 3) == 0) {
+#pragma unroll
+                for (int k = 0; k < K; ++k) bq[k] = bsrc.quad(k, blk * (RU / 4) + (rr >> 2));
+            }
+            uint32_t bw[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) bw[k] = (rr & 3) == 0 ? bq[k].x : (rr & 3) == 1 ? bq[k].y : (rr & 3) == 2 ? bq[k].z : bq[k].w;
+            uint32_t nE[NLIMB + 1], nO[NLIMB];
+            const uint32_t b0 = bw[0];
+            // T >>= 32 folded into this row (see fq_dot)
+            nE[0] = prim::add_cc(O[0], E[1]);
+#pragma unroll
+            for (int j = 1; j < NLIMB; j += 2) {
+                nO[j - 1] = prim::madc_lo_cc(a[0][j], b0, E[j + 1]);
+                nO[j] = prim::madc_hi_cc(a[0][j], b0, (j + 2 <= NLIMB) ? E[(j + 2 <= NLIMB) ? j + 2 : 0] : 0u);
+            }
+            nE[0] = prim::mad_lo_cc(a[0][0], b0, nE[0]);
+            nE[1] = prim::madc_hi_cc(a[0][0], b0, O[1]);
+#pragma unroll
+            for (int j = 2; j < NLIMB; j += 2) {
+                nE[j] = prim::madc_lo_cc(a[0][j], b0, O[j]);
+                nE[j + 1] = prim::madc_hi_cc(a[0][j], b0, O[j + 1]);
+            }
+            nE[NLIMB] = prim::addc(0, 0);
+#pragma unroll
+            for (int j = 0; j <= NLIMB; ++j) E[j] = nE[j];
+#pragma unroll
+            for (int j = 0; j < NLIMB; ++j) O[j] = nO[j];
+#pragma unroll
+            for (int k = 1; k < K; ++k) {
+                const uint32_t bk = bw[k];
+                E[0] = prim::mad_lo_cc(a[k][0], bk, E[0]);
+                E[1] = prim::madc_hi_cc(a[k][0], bk, E[1]);
+#pragma unroll
+                for (int j = 2; j < NLIMB; j += 2) {
+                    E[j] = prim::madc_lo_cc(a[k][j], bk, E[j]);
+                    E[j + 1] = prim::madc_hi_cc(a[k][j], bk, E[j + 1]);
+                }
+                E[NLIMB] = prim::addc(E[NLIMB], 0);
+                O[0] = prim::mad_lo_cc(a[k][1], bk, O[0]);
+                O[1] = prim::madc_hi_cc(a[k][1], bk, O[1]);
+#pragma unroll
+                for (int j = 3; j < NLIMB; j += 2) {
+                    O[j - 1] = prim::madc_lo_cc(a[k][j], bk, O[j - 1]);
+                    O[j] = prim::madc_hi_cc(a[k][j], bk, O[j]);
+                }
+            }
+            const uint32_t m = prim::mul_lo(E[0], M::INV);
+            E[0] = prim::mad_lo_cc(m, M::P(0), E[0]);
+            E[1] = prim::madc_hi_cc(m, M::P(0), E[1]);
+#pragma unroll
+            for (int j = 2; j < NLIMB; j += 2) {
+                E[j] = prim::madc_lo_cc(m, M::P(j), E[j]);
+                E[j + 1] = prim::madc_hi_cc(m, M::P(j), E[j + 1]);
+            }
+            E[NLIMB] = prim::addc(E[NLIMB], 0);
+            O[0] = prim::mad_lo_cc(m, M::P(1), O[0]);
+            O[1] = prim::madc_hi_cc(m, M::P(1), O[1]);
+#pragma unroll
+            for (int j = 3; j < NLIMB; j += 2) {
+                O[j - 1] = prim::madc_lo_cc(m, M::P(j), O[j - 1]);
+                O[j] = prim::madc_hi_cc(m, M::P(j), O[j]);
+            }
+        }
+    }
+    fq_t t;
+    t[0] = prim::add_cc(O[0], E[1]);
+#pragma unroll
+    for (int k = 1; k < NLIMB; ++k) t[k] = prim::addc_cc(O[k], E[k + 1]);
+    fq_cond_sub<M>(r, t);
+}
+
 // ---- reduced-radix dot product (EXPERIMENT, not used by the engine) ------------------------------
 // Same contract as fq_dot, different instruction mix: the product is evaluated in radix 2^W, W < 32,
 // so that every partial product is a carry-free IMAD.WIDE.U32 into a 64-bit column accumulator that
@@ -391,6 +484,12 @@ MSM_DEVICE void fq_from_mont(fq_t &r, const fq_t &a) {
     for (int i = 0; i < NLIMB; ++i) one[i] = (i == 0) ? 1u : 0u;
     fq_mul<M>(r, a, one);
 }
+
+#ifdef MNT753_HOST_EMU
+#define MSM_COLD inline
+#else
+#define MSM_COLD __device__ __noinline__
+#endif
 
 // ---- modular inversion (binary extended Euclid, one thread) ------------------------------------
 // The reference has no inversion on the device (multiexp/arith.cu:347-354 is #if 0); the CPU side
@@ -647,11 +746,6 @@ MSM_DEVICE bool fq_inv_plain_fast(fq_t &r, const fq_t &y) {
 // Montgomery-form inverse: a = xR -> x^-1 R  (0 -> 0, like the oracle's field inversion).
 // A real function on the device, with a single copy of the multiplier and a cold fallback, to keep the
 // rarely executed inversion from evicting the hot loops out of the instruction cache.
-#ifdef MNT753_HOST_EMU
-#define MSM_COLD inline
-#else
-#define MSM_COLD __device__ __noinline__
-#endif
 template <class M>
 MSM_COLD bool fq_inv_plain_cold(fq_t &r, const fq_t &a) { return fq_inv_plain<M>(r, a); }
 template <class M>

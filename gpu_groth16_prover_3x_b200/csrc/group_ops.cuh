@@ -552,10 +552,52 @@ int run_synthetic(b200msm_ctx *ctx, size_t n, const uint64_t *k_p0, const uint64
     return B200MSM_OK;
 }
 
+// throughput of the slab multiplier (Team::mul, operands in shared memory) at 4 / 8 / 12 warps per SM:
+// `iters` x 2 dependent products per lane.  Returns 10^9 Fq-tower products per second in *gops.
+template <class G>
+__global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_mb_teammul(int iters, uint32_t *out) {
+    typedef typename G::F F;
+    typedef BaCfg<G> C;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    T.set_one(0);
+    T.set_one(1);
+    T.dbl(1, 1);
+    T.sync();
+    for (int it = 0; it < iters; ++it) { T.mul(0, 0, 1); T.mul(1, 1, 0); }
+    T.sync();
+    if (T.is_zero(0) && out) out[0] = 1;
+}
+
+template <class G>
+int run_teammul_bench(b200msm_ctx *ctx, int blocks_per_sm, int iters, double *gops) {
+    typedef BaCfg<G> C;
+    CU(cudaFuncSetAttribute(k_mb_teammul<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TS::SMEM));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    const int blocks = ctx->sm_count * blocks_per_sm;
+    for (int rep = 0; rep < 2; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        k_mb_teammul<G><<<blocks, C::TS::THREADS, C::TS::SMEM>>>(iters, nullptr);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+    }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    CU(cudaGetLastError());
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *gops = double(blocks) * C::TPB * 32 * 2.0 * iters / (double(ms) * 1e6);
+    return B200MSM_OK;
+}
+
 }  // namespace
 
 
 template <class G>
 constexpr GroupOps make_group_ops() {
-    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>};
+    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>, &run_teammul_bench<G>};
 }

@@ -143,4 +143,5 @@ struct GroupOps {
     int (*to_affine)(b200msm_ctx *, size_t, const uint64_t *, uint64_t *);
     int (*synthetic)(b200msm_ctx *, size_t, const uint64_t *, const uint64_t *, BaseSet &);
     int (*build_tables)(b200msm_ctx *, BaseSet &);
+    int (*teammul_bench)(b200msm_ctx *, int, int, double *);
 };

@@ -356,8 +356,13 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
 
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     if (!ctx) return B200MSM_ERR_ARG;
-    if (!gops || iters <= 0 || kind < 0 || kind > 6) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    if (!gops || iters <= 0 || kind < 0 || kind > 18) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
+    if (kind >= 7) {  // slab multiplier: kind = 7 + 4 * (group - 1) + (blocks per SM - 1), blocks per SM in 1..4
+        const int group = kind < 11 ? B200MSM_G1 : B200MSM_G2, bps = (kind - 7) % 4 + 1;
+        if (kind > 14) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+        return ops_for(ctx->curve, group).teammul_bench(ctx, bps, iters, gops);
+    }
     uint32_t *d = nullptr;
     CU(cudaMalloc(&d, 256));
     cudaEvent_t e0, e1;

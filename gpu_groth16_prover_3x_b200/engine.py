@@ -30,7 +30,9 @@ def degree(curve, group):
 
 
 def library_path():
-    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200msm.so")
+    """In-tree libb200msm.so; B200MSM_LIB overrides it with another build of the SAME library (A/B runs of
+    kernel variants during development).  There is no other implementation to fall back to."""
+    return os.environ.get("B200MSM_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libb200msm.so")
 
 
 def load_library():

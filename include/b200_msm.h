@@ -126,7 +126,9 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
  *       3 = the reduced-radix (29-bit limbs, carry-free IMAD.WIDE.U32) experiment, for comparison;
  *       4, 5, 6 = latency of one Fq inversion by a single thread, in MICROSECONDS (not a rate): the engine's
  *           fq_inv, the plain binary gcd, the approximation-based fast path alone (fails if it ever needs
- *           the fallback). */
+ *           the fallback);
+ *       7..10 (G1) / 11..14 (G2) = the slab multiplier Team::mul (operands in shared memory, as used by
+ *           every curve operation) with 1..4 resident blocks per SM; returns 10^9 tower products/s. */
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops);
 
 /* Self-test hooks (used by tests/ only): the device field / point layer applied elementwise.
