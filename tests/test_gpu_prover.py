@@ -1,0 +1,43 @@
+"""End-to-end acceptance test of the reference's README: the proof written by the GPU prover must have the
+same sha256 as the one written by the reference's CPU prover (`main <curve> compute`) on the same freshly
+generated parameters and input.  Here the "GPU prover" is the reference's own driver with its five MSMs routed
+through libb200msm.so (tests/integration/b200_prover.cpp, built into oracle/_ref/ by `make -C oracle prover`
+where /root/reference exists; the binaries travel to the GPU box with the snapshot)."""
+import hashlib
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref")
+BINS = [os.path.join(REF, b) for b in ("generate_parameters", "main", "b200_prover")]
+
+
+def sha256(path):
+    return hashlib.sha256(open(path, "rb").read()).hexdigest()
+
+
+@pytest.fixture(scope="module")
+def fast_params(tmp_path_factory):
+    if not all(os.path.exists(b) for b in BINS):
+        pytest.skip("reference binaries not built (oracle/_ref): run __graft_entry__.build() where /root/reference exists")
+    d = tmp_path_factory.mktemp("groth16")
+    # `generate_parameters fast`: MNT4753 d = 2^14 - 1, MNT6753 d = 2^10 - 1 (generate_parameters.cpp:110-135)
+    subprocess.run([BINS[0], "fast"], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=900)
+    return d
+
+
+@pytest.mark.parametrize("curve", ["MNT4753", "MNT6753"])
+def test_proof_sha256_equals_reference_cpu_prover(fast_params, curve):
+    d = fast_params
+    params, inp = "%s-parameters" % curve, "%s-input" % curve
+    subprocess.run([BINS[1], curve, "compute", params, inp, curve + "-output-ref"], cwd=d, check=True,
+                   stdout=subprocess.DEVNULL, timeout=1800)
+    out = subprocess.run([BINS[2], curve, "compute", params, inp, curve + "-output-b200"], cwd=d, check=True,
+                         capture_output=True, text=True, timeout=900).stdout
+    print(out)
+    a, b = os.path.join(d, curve + "-output-ref"), os.path.join(d, curve + "-output-b200")
+    assert os.path.getsize(a) == os.path.getsize(b) == (768 if curve == "MNT4753" else 960)
+    assert sha256(a) == sha256(b)
