@@ -237,6 +237,24 @@ struct Team {
             } else st(d, c, x);
         }
     }
+    // d = 1 / a on EVERY lane (a != 0): the lanes run the binary gcd side by side (divergent, but the
+    // alternative -- Fermat's a^(q-2), 750 squarings through the multiplier -- costs ten times more).  Used by
+    // the affine normalisations (util_kernels.cuh), one inversion per lane and run of points.
+    MSM_OP void inv_all(int d, int a, int t0, int t1) const {
+        if (DEG == 1) {
+            MSM_FOR_COMP(c) { fq_t x, r; ld(x, a, c); fq_inv<M>(r, x); st(d, c, r); }
+            return;
+        }
+        frob(t0, a, 1);
+        if (DEG == 3) { frob(t1, a, 2); mul(t0, t0, t1); }
+        mul(t1, a, t0);                      // norm, lies in Fq: (N, 0[, 0])
+#ifdef MNT753_HOST_EMU
+        { fq_t x, r; ld(x, t1, 0); fq_inv<M>(r, x); st(t1, 0, r); }
+#else
+        if (comp == 0) { fq_t x, r; ld(x, t1, 0); fq_inv<M>(r, x); st(t1, 0, r); }
+#endif
+        mul(d, t0, t1);
+    }
     // d = 1 / a for the element of LANE 0 only (other lanes: unspecified); a != 0.  t0, t1 scratch, all
     // four slots distinct.  One binary-gcd inversion in Fq by a single thread; for the towers the element is
     // first reduced to its norm:  a^-1 = conj(a) / N(a),  conj(a) = prod of the non-trivial Frobenius images.

@@ -159,18 +159,40 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
 
     uint64_t launches = 0;
     CU(cudaEventRecord(ln.ev[0], st));
-    CU(cudaMemcpyAsync(a.scalars, scalars, n * NLIMB * 4, cudaMemcpyDefault, st));
-    CU(cudaEventRecord(ln.ev[1], st));
-
-    const unsigned nb128 = (unsigned)((n + 127) / 128), nb256 = (unsigned)((n + 255) / 256);
-    k_from_mont<typename G::Fr><<<nb128, 128, 0, st>>>(a.scalars, a.n);
+    // Scalars: device-resident ones are copied in one piece; host scalars are uploaded in chunks on the lane's
+    // copy stream so that the de-Montgomery + digit histogram of chunk k overlap the PCIe transfer of chunk k+1.
+    cudaPointerAttributes pattr;
+    const bool on_device = cudaPointerGetAttributes(&pattr, scalars) == cudaSuccess && pattr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    const int nchunk = (!on_device && n >= (size_t(1) << 16)) ? NCOPY : 1;
     CU(cudaMemsetAsync(a.count, 0, (size_t)a.K * 4, st));
-    k_count<<<nb256, 256, 0, st>>>(a);
+    if (nchunk > 1) {
+        CU(cudaEventRecord(ln.ev_copy[NCOPY], st));                 // the arena is free once earlier work on st is done
+        CU(cudaStreamWaitEvent(ln.copy_stream, ln.ev_copy[NCOPY], 0));
+    }
+    for (int ch = 0; ch < nchunk; ++ch) {
+        const size_t lo = n * ch / nchunk, hi = n * (ch + 1) / nchunk;
+        if (nchunk > 1) {
+            CU(cudaMemcpyAsync(a.scalars + lo * NLIMB, (const uint32_t *)scalars + lo * NLIMB, (hi - lo) * NLIMB * 4, cudaMemcpyDefault, ln.copy_stream));
+            CU(cudaEventRecord(ln.ev_copy[ch], ln.copy_stream));
+            CU(cudaStreamWaitEvent(st, ln.ev_copy[ch], 0));
+        } else {
+            CU(cudaMemcpyAsync(a.scalars, scalars, n * NLIMB * 4, cudaMemcpyDefault, st));
+            CU(cudaEventRecord(ln.ev[1], st));
+        }
+        k_from_mont<typename G::Fr><<<(unsigned)((hi - lo + 127) / 128), 128, 0, st>>>(a.scalars + lo * NLIMB, (uint32_t)(hi - lo));
+        a.i0 = (uint32_t)lo;
+        a.i1 = (uint32_t)hi;
+        k_count<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>(a);
+        launches += 2;
+    }
+    if (nchunk > 1) CU(cudaEventRecord(ln.ev[1], st));    // chunked: "H2D" is folded into recode+sort
+    const unsigned nb256 = (unsigned)((n + 255) / 256);
     k_scan_local<<<p.nscan, SCAN_T, 0, st>>>(a.count, a.offs, p.bsum, a.K);
     k_scan_bsum<<<1, SCAN_T, 0, st>>>(p.bsum, p.nscan, a.offs + a.K);
     k_scan_add<<<p.nscan, SCAN_T, 0, st>>>(a.offs, a.cursor, p.bsum, a.K);
     k_scatter<<<nb256, 256, 0, st>>>(a);
-    launches += 6;
+    launches += 4;
     CU(cudaEventRecord(ln.ev[2], st));
 
     const unsigned tail_lanes = TC::TPB * 32;
@@ -408,62 +430,22 @@ int run_fold(b200msm_ctx *ctx, const uint64_t *xyz, size_t n, uint64_t *out) {
 }
 
 // ---- affine normalisation / synthetic bases ---------------------------------------------------
-// exponent q^DEG - 2 of the Fermat inversion in Fq^DEG, little-endian 32-bit words
-template <class G>
-std::vector<uint32_t> fermat_exponent() {
-    constexpr int DEG = G::F::DEG;
-    std::vector<uint32_t> q(NLIMB), acc(1, 1u);
-    for (int i = 0; i < NLIMB; ++i) q[i] = G::F::M::P(i);
-    for (int d = 0; d < DEG; ++d) {
-        std::vector<uint32_t> r(acc.size() + NLIMB, 0u);
-        for (size_t i = 0; i < acc.size(); ++i) {
-            uint64_t carry = 0;
-            for (int j = 0; j < NLIMB; ++j) {
-                uint64_t t = (uint64_t)acc[i] * q[j] + r[i + j] + carry;
-                r[i + j] = (uint32_t)t;
-                carry = t >> 32;
-            }
-            r[i + NLIMB] = (uint32_t)carry;
-        }
-        acc.swap(r);
-    }
-    uint64_t borrow = 2;  // acc -= 2 (q is odd and > 2, so no underflow)
-    for (size_t i = 0; i < acc.size() && borrow; ++i) {
-        uint64_t t = (uint64_t)acc[i] - borrow;
-        acc[i] = (uint32_t)t;
-        borrow = (t >> 63) & 1u;
-    }
-    return acc;
-}
-
 struct DevBuf {
     void *p = nullptr;
     ~DevBuf() { if (p) cudaFree(p); }
 };
 
 template <class G>
-int upload_exponent(b200msm_ctx *ctx, DevBuf &d, int &bits) {
-    std::vector<uint32_t> e = fermat_exponent<G>();
-    bits = G::F::DEG * MNT753_NUM_BITS;
-    CU(cudaMalloc(&d.p, e.size() * 4));
-    CU(cudaMemcpy(d.p, e.data(), e.size() * 4, cudaMemcpyHostToDevice));
-    return B200MSM_OK;
-}
-
-template <class G>
 int run_to_affine(b200msm_ctx *ctx, size_t n, const uint64_t *xyz, uint64_t *out) {
     typedef TailCfg<G> TC;
     constexpr size_t EB = G::F::DEG * NLIMB * 4;
-    DevBuf e, in, o;
-    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
-    if (rc) return rc;
+    DevBuf in, o;
     CU(cudaMalloc(&in.p, n * 3 * EB));
     CU(cudaMalloc(&o.p, n * 2 * EB));
     CU(cudaMemcpy(in.p, xyz, n * 3 * EB, cudaMemcpyDefault));
     CU(cudaFuncSetAttribute(k_to_affine<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
     const unsigned lanes = TC::TPB * 32;
-    k_to_affine<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, (const uint32_t *)in.p, (uint32_t *)o.p,
-                                                                                         (const uint32_t *)e.p, bits);
+    k_to_affine<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, (const uint32_t *)in.p, (uint32_t *)o.p);
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(out, o.p, n * 2 * EB, cudaMemcpyDefault));
@@ -485,9 +467,7 @@ int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
     constexpr size_t EB = G::F::DEG * NLIMB * 4;
     constexpr uint32_t B = 32;
     if (bs.NT <= 1 || bs.n == 0) return B200MSM_OK;
-    DevBuf e, jac, pre;
-    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
-    if (rc) return rc;
+    DevBuf jac, pre;
     const size_t n = bs.n;
     CU(cudaMalloc(&jac.p, n * 3 * EB));
     CU(cudaMalloc(&pre.p, n * EB));
@@ -504,7 +484,7 @@ int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
         k_dbl_many<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, bs.c_tab * bs.G, bs.pts + (t - 1) * tabw,
                                                                                             (uint32_t *)jac.p);
         k_batch_normalise<G><<<(unsigned)((runs + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>(
-            (uint32_t)n, B, (const uint32_t *)jac.p, (uint32_t *)pre.p, bs.pts + t * tabw, (const uint32_t *)e.p, bits);
+            (uint32_t)n, B, (const uint32_t *)jac.p, (uint32_t *)pre.p, bs.pts + t * tabw);
     }
     CU(cudaEventRecord(e1, 0));
     CU(cudaGetLastError());
@@ -521,9 +501,7 @@ int run_synthetic(b200msm_ctx *ctx, size_t n, const uint64_t *k_p0, const uint64
     typedef TailCfg<G> TC;
     constexpr size_t EB = G::F::DEG * NLIMB * 4;
     constexpr uint32_t B = 64;
-    DevBuf e, gen, ks, pj, pa, jac, pre;
-    int bits = 0, rc = upload_exponent<G>(ctx, e, bits);
-    if (rc) return rc;
+    DevBuf gen, ks, pj, pa, jac, pre;
     CU(cudaMalloc(&gen.p, 2 * EB));
     CU(cudaMalloc(&ks.p, 2 * NLIMB * 4));
     CU(cudaMalloc(&pj.p, 2 * 3 * EB));
@@ -539,12 +517,11 @@ int run_synthetic(b200msm_ctx *ctx, size_t n, const uint64_t *k_p0, const uint64
     for (int i = 0; i < 2; ++i)
         k_scalar_mul<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>((const uint32_t *)gen.p, (const uint32_t *)ks.p + i * NLIMB,
                                                              (uint32_t *)pj.p + i * 3 * (EB / 4));
-    k_to_affine<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>(2u, (const uint32_t *)pj.p, (uint32_t *)pa.p, (const uint32_t *)e.p, bits);
+    k_to_affine<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>(2u, (const uint32_t *)pj.p, (uint32_t *)pa.p);
     const unsigned lanes = TC::TPB * 32;
     const size_t runs = (n + B - 1) / B;
     k_synth_bases<G><<<(unsigned)((runs + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>(
-        (uint32_t)n, B, (const uint32_t *)pa.p, (const uint32_t *)pa.p + 2 * (EB / 4), bs.pts, (uint32_t *)jac.p, (uint32_t *)pre.p,
-        (const uint32_t *)e.p, bits);
+        (uint32_t)n, B, (const uint32_t *)pa.p, (const uint32_t *)pa.p + 2 * (EB / 4), bs.pts, (uint32_t *)jac.p, (uint32_t *)pre.p);
     constexpr int DEG = G::F::DEG;
     k_flag_inf<DEG><<<(unsigned)((n + 255) / 256), 256>>>(bs.pts, (uint32_t)n, bs.inf);
     CU(cudaGetLastError());

@@ -18,6 +18,7 @@ using namespace mnt753;
 
 constexpr int NLANES = 4;
 constexpr int NEVENTS = 7;
+constexpr int NCOPY = 4;     // chunks of a host-scalar upload
 
 // A resident base set.  Besides the points themselves (table 0) it may hold NT - 1 further
 // "window tables": table t = 2^(c*G*t) * P_i, affine, row t*n + i of `pts`.  Signed digit w of a
@@ -42,6 +43,8 @@ struct Lane {
     cudaStream_t stream = nullptr;      // stream MSMs are enqueued on
     cudaStream_t own_stream = nullptr;  // the lane's internal stream (stream == own_stream unless overridden)
     cudaEvent_t ev[NEVENTS] = {};
+    cudaStream_t copy_stream = nullptr;       // H2D of host scalars, overlapped with the recode of earlier chunks
+    cudaEvent_t ev_copy[NCOPY + 1] = {};
     char *arena = nullptr;
     size_t arena_bytes = 0;
     uint32_t *h_result = nullptr;  // pinned staging for the Jacobian result

@@ -182,6 +182,8 @@ int b200msm_create(int curve, int device, b200msm_ctx **out) {
         bool ok = cudaStreamCreateWithFlags(&ln.own_stream, cudaStreamNonBlocking) == cudaSuccess;
         ln.stream = ln.own_stream;
         for (int e = 0; e < NEVENTS && ok; ++e) ok = cudaEventCreate(&ln.ev[e]) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithFlags(&ln.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
+        for (int e = 0; e <= NCOPY && ok; ++e) ok = cudaEventCreateWithFlags(&ln.ev_copy[e], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_result, 3 * 3 * NLIMB * 4) == cudaSuccess;
         if (!ok) { b200msm_destroy(ctx); return B200MSM_ERR_CUDA; }
     }
@@ -198,6 +200,8 @@ void b200msm_destroy(b200msm_ctx *ctx) {
         if (ln.arena) cudaFree(ln.arena);
         if (ln.h_result) cudaFreeHost(ln.h_result);
         for (int e = 0; e < NEVENTS; ++e) if (ln.ev[e]) cudaEventDestroy(ln.ev[e]);
+        for (int e = 0; e <= NCOPY; ++e) if (ln.ev_copy[e]) cudaEventDestroy(ln.ev_copy[e]);
+        if (ln.copy_stream) cudaStreamDestroy(ln.copy_stream);
         if (ln.own_stream) cudaStreamDestroy(ln.own_stream);
     }
     for (auto &s : ctx->sets) if (s.used) { cudaFree(s.pts); cudaFree(s.inf); }

@@ -28,6 +28,7 @@ constexpr uint32_t EDGE_NONE = 0xffffffffu;
 struct MsmArgs {
     // problem
     uint32_t n;        // number of points
+    uint32_t i0, i1;   // k_count: range of points handled by this launch (scalar upload is chunked)
     int c;             // window width in bits
     int Wd;            // number of signed digits (windows) per scalar = ceil(754 / c)
     int W;             // number of bucket sets = ceil(Wd / NT): digit w lands in set w % W, using table w / W
@@ -176,8 +177,8 @@ __device__ __forceinline__ void for_each_digit(const uint32_t *k, int c, int W, 
 }
 
 static __global__ void k_count(MsmArgs a) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n || a.base_inf[i]) return;
+    uint32_t i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.i1 || a.base_inf[i]) return;
     uint32_t k[NLIMB];
     const uint4 *p = reinterpret_cast<const uint4 *>(a.scalars + (size_t)i * NLIMB);
     for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w; }

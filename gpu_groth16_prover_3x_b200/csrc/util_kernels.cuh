@@ -1,4 +1,4 @@
-// Device-side utilities around the MSM: affine normalisation (one Fermat inversion per lane, shared by
+// Device-side utilities around the MSM: affine normalisation (one binary-gcd inversion per lane, shared by
 // a whole batch through Montgomery's trick), scalar multiplication of a single point, and the
 // synthetic base generator  P_i = P0 + i*Q  of SURVEY.md 8(d) (the structured bases whose MSM has a
 // closed form), produced directly in HBM so that benchmark inputs never cross PCIe.
@@ -10,16 +10,6 @@
 #include "msm_kernels.cuh"
 
 namespace mnt753 {
-
-// dst = base^e, e given as little-endian 32-bit words (uniform over the grid); dst != base.
-template <class F>
-__device__ void team_pow(const Team<F> &T, int dst, int base, const uint32_t *e, int nbits) {
-    T.set_one(dst);
-    for (int bit = nbits - 1; bit >= 0; --bit) {
-        T.sqr(dst, dst);
-        if ((e[bit >> 5] >> (bit & 31)) & 1u) T.mul(dst, dst, base);
-    }
-}
 
 struct UtilSlots {
     static constexpr int X1 = 0, Y1 = 1, Z1 = 2, X2 = 3, Y2 = 4, Z2 = 5, T0 = 6, T1 = 7, T2 = 8, PRE = 9, INV = 10, TMP = 11;
@@ -41,10 +31,10 @@ __device__ void small_scalar_mul(const Team<F> &T, const PtSlots &s, uint32_t k,
 // prefix[idx] the inclusive prefix products; writes affine(jac[idx]) to out (infinity -> all zero).
 template <class F>
 __device__ void normalise_run(const Team<F> &T, uint32_t start, uint32_t B, uint32_t n, bool valid, const uint32_t *jac,
-                              const uint32_t *prefix, uint32_t *out, const uint32_t *e, int ebits) {
+                              const uint32_t *prefix, uint32_t *out) {
     typedef UtilSlots U;
     constexpr int EW = F::DEG * NLIMB, AFFW = 2 * EW, JACW = 3 * EW;
-    team_pow(T, U::INV, U::PRE, e, ebits);
+    T.inv_all(U::INV, U::PRE, U::T0, U::T1);
     for (int j = (int)B - 1; j >= 0; --j) {
         const uint32_t idx = start + (uint32_t)j;
         const bool act = valid && idx < n;
@@ -75,8 +65,7 @@ __device__ void normalise_run(const Team<F> &T, uint32_t start, uint32_t B, uint
 // out[i] = affine(P0 + i*Q), i < n.  One lane per run of B consecutive indices.
 template <class G>
 __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_synth_bases(uint32_t n, uint32_t B, const uint32_t *p0, const uint32_t *q,
-                                                                         uint32_t *out, uint32_t *jac, uint32_t *prefix,
-                                                                         const uint32_t *e, int ebits) {
+                                                                         uint32_t *out, uint32_t *jac, uint32_t *prefix) {
     typedef typename G::F F;
     typedef TailCfg<G> C;
     typedef UtilSlots U;
@@ -117,7 +106,7 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_synth_bases(uint32_
         s2g(T, prefix + (size_t)idx * EW, U::PRE, act);
         Ec<F>::madd(T, s, false, act, acc_inf);
     }
-    normalise_run<F>(T, start, B, n, valid, jac, prefix, out, e, ebits);
+    normalise_run<F>(T, start, B, n, valid, jac, prefix, out);
 }
 
 // ---- precomputed window tables -------------------------------------------------------------------
@@ -145,10 +134,10 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_dbl_many(uint32_t n
     store_jac(T, jac + (size_t)id * 3 * EW, U::X1, U::Y1, U::Z1, act);
 }
 
-// out[i] = affine(jac[i]), i < n: one lane per run of B consecutive points, one Fermat inversion per lane.
+// out[i] = affine(jac[i]), i < n: one lane per run of B consecutive points, one inversion per lane.
 template <class G>
 __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_batch_normalise(uint32_t n, uint32_t B, const uint32_t *jac, uint32_t *prefix,
-                                                                             uint32_t *out, const uint32_t *e, int ebits) {
+                                                                             uint32_t *out) {
     typedef typename G::F F;
     typedef TailCfg<G> C;
     typedef UtilSlots U;
@@ -175,12 +164,12 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_batch_normalise(uin
         s2g(T, prefix + (size_t)idx * EW, U::PRE, act);
     }
     T.sync();
-    normalise_run<F>(T, start, B, n, valid, jac, prefix, out, e, ebits);
+    normalise_run<F>(T, start, B, n, valid, jac, prefix, out);
 }
 
 // out[i] = affine(jac[i]) in the wire format (infinity -> all zero), one lane per point.
 template <class G>
-__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_to_affine(uint32_t n, const uint32_t *jac, uint32_t *out, const uint32_t *e, int ebits) {
+__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_to_affine(uint32_t n, const uint32_t *jac, uint32_t *out) {
     typedef typename G::F F;
     typedef TailCfg<G> C;
     typedef UtilSlots U;
@@ -196,7 +185,7 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_to_affine(uint32_t 
     T.sync();
     const bool inf = T.is_zero(U::Z1);
     T.set_one(U::Z1, inf);
-    team_pow(T, U::INV, U::Z1, e, ebits);
+    T.inv_all(U::INV, U::Z1, U::T0, U::T2);
     T.sqr(U::T1, U::INV);
     T.mul(U::X1, U::X1, U::T1);
     T.mul(U::T1, U::T1, U::INV);
