@@ -262,14 +262,27 @@ def run_b200(args):
     peak = max(micro["imad_wide_gmacs"], micro["fq_modmul_gmuls"] * 1176)
     hbm_peak, hbm_src = measured_hbm_peak()
     aff_bytes = 2 * deg * 96
-    alg_bytes = float(n) * W * (aff_bytes + 4)
+    if muls_per_add == 6:
+        # batched-affine addition: forward reads x1, x2 and parks the prefix; backward reads both points and the
+        # prefix and writes the sum; the pair descriptor (16 B) is read in both passes
+        alg_bytes = float(n) * W * (2 * 96 * deg + 96 * deg + 2 * aff_bytes + 96 * deg + aff_bytes + 32 + 2)
+    else:
+        alg_bytes = float(n) * W * (aff_bytes + 4)
+    traffic = None
+    try:
+        if (curve, group, args.log_n) == (0, 1, 20) and muls_per_add == 6:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_k_batch_add_round0_traffic.json")))
+            traffic = {"bytes": tj["traffic_bytes"], "launch": tj["kernel"], "source": tj["source"],
+                       "algorithmic_bytes_of_that_launch": float(n) * W / 2 * (alg_bytes / (float(n) * W))}
+    except Exception:
+        traffic = None
     # SURVEY.md 8(d) canonical count (c = 16, W = 48, Jacobian mixed add) applied to the whole step: what the
     # reference-style algorithm would have to execute to deliver the same points/s
     canonical_macs_per_point = 1176.0 * 11 * k_tower * 48
     roofline = {
         "kernel": "k_batch_add (all rounds of one MSM)" if muls_per_add == 6 else "k_accumulate", "bound": "imad",
         "field_muls_per_addition": muls_per_add, "achieved": achieved, "peak": peak, "unit": "GMAC/s", "frac": achieved / peak,
-        "traffic": None, "launch_ms": acc_ms, "share_of_step": acc_ms / (dev_s / args.steps * 1e3),
+        "traffic": traffic, "launch_ms": acc_ms, "share_of_step": acc_ms / (dev_s / args.steps * 1e3),
         "peak_source": "measured in this run: max(IMAD.WIDE.U32 stream, Fq Montgomery product in registers x 1176 MAC); "
                        "a 32x32->64 multiply-add issues at 32 per clock per SM on B200 (tools/pipe_probe.cu)",
         "macs_per_launch": macs_per_launch, "micro": micro,

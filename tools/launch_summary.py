@@ -5,10 +5,14 @@ rows = list(csv.reader(open(sys.argv[1])))
 hdr = [i for i, r in enumerate(rows) if r and r[0] == 'ID'][0]
 rows = rows[hdr + 1:]
 names = [re.sub(r'\(.*', '', r[4]).replace('void ', '').replace('mnt753::', '') for r in rows]
-starts = [i for i, n in enumerate(names) if n.startswith('k_from_mont')]
-s = starts[-1]
+# an MSM starts with its (possibly chunked) k_from_mont / k_count launches and has exactly one k_scatter
+end = max(i for i, n in enumerate(names) if n.startswith('k_horner'))     # last COMPLETE MSM
+last_scatter = max(i for i, n in enumerate(names[:end]) if n.startswith('k_scatter'))
+s = last_scatter
+while s > 0 and (names[s - 1].startswith('k_from_mont') or names[s - 1].startswith('k_count') or names[s - 1].startswith('k_scan')):
+    s -= 1
 agg, seq, tot = {}, [], 0.0
-for r, n in zip(rows[s:], names[s:]):
+for r, n in zip(rows[s:end + 1], names[s:end + 1]):
     t = float(r[-1]) / 1e6
     tot += t
     agg[n] = agg.get(n, 0) + t
