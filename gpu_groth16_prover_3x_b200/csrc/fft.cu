@@ -1,0 +1,135 @@
+// C ABI of the H-polynomial path (include/b200_msm.h: b200msm_compute_h): host side of fft_kernels.cuh.
+// Replaces compute_H<B> (cuda_prover_piecewise.cu:14-49), i.e. B::domain_iFFT / domain_cosetFFT /
+// vector_Fr_muleq / vector_Fr_subeq / domain_divide_by_Z_on_coset / domain_icosetFFT
+// (prover_reference_functions.cpp) on libfqfft's basic_radix2_domain.
+#include "host_ctx.cuh"
+#include "fft_kernels.cuh"
+
+namespace {
+
+void fft_free(FftState &f) {
+    for (uint32_t **p : {&f.consts, &f.tw, &f.twi, &f.cg_br, &f.cgi_br, &f.a, &f.b, &f.c, &f.out}) {
+        if (*p) cudaFree(*p);
+        *p = nullptr;
+    }
+    f.logm = -1;
+}
+
+template <class M>
+int fft_prepare(b200msm_ctx *ctx, int logm) {
+    FftState &f = ctx->fft;
+    if (!f.stream) {
+        CU(cudaStreamCreateWithFlags(&f.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreate(&f.ev[0]));
+        CU(cudaEventCreate(&f.ev[1]));
+    }
+    if (f.logm == logm) return B200MSM_OK;
+    fft_free(f);
+    const size_t m = size_t(1) << logm, EB = NLIMB * 4;
+    CU(cudaMalloc(&f.consts, FC_COUNT * EB));
+    CU(cudaMalloc(&f.tw, std::max<size_t>(m / 2, 1) * EB));
+    CU(cudaMalloc(&f.twi, std::max<size_t>(m / 2, 1) * EB));
+    CU(cudaMalloc(&f.cg_br, m * EB));
+    CU(cudaMalloc(&f.cgi_br, m * EB));
+    CU(cudaMalloc(&f.a, m * EB));
+    CU(cudaMalloc(&f.b, m * EB));
+    CU(cudaMalloc(&f.c, m * EB));
+    CU(cudaMalloc(&f.out, (m + 1) * EB));
+    cudaStream_t st = f.stream;
+    CU(cudaEventRecord(f.ev[0], st));
+    k_fft_consts<M><<<1, 32, 0, st>>>(f.consts, logm);
+    const uint32_t *C = f.consts;
+    const unsigned gh = (unsigned)((m / 2 + 127) / 128), gm = (unsigned)((m + 127) / 128);
+    if (m >= 2) {
+        k_powers<M><<<gh, 128, 0, st>>>(f.tw, (uint32_t)(m / 2), C + FC_OMEGA * NLIMB, C + FC_ONE * NLIMB, 0);
+        k_powers<M><<<gh, 128, 0, st>>>(f.twi, (uint32_t)(m / 2), C + FC_OMEGA_INV * NLIMB, C + FC_ONE * NLIMB, 0);
+    }
+    k_powers<M><<<gm, 128, 0, st>>>(f.cg_br, (uint32_t)m, C + FC_G * NLIMB, C + FC_M_INV * NLIMB, logm);
+    k_powers<M><<<gm, 128, 0, st>>>(f.cgi_br, (uint32_t)m, C + FC_G_INV * NLIMB, C + FC_M_INV * NLIMB, logm);
+    CU(cudaEventRecord(f.ev[1], st));
+    CU(cudaGetLastError());
+    CU(cudaEventSynchronize(f.ev[1]));
+    CU(cudaEventElapsedTime(&f.tables_ms, f.ev[0], f.ev[1]));
+    f.logm = logm;
+    return B200MSM_OK;
+}
+
+template <class M>
+void ifft_dif(const FftState &f, uint32_t *x, uint32_t m) {   // natural in, bit-reversed out, NOT yet scaled by 1/m
+    for (uint32_t len = m; len >= 2; len >>= 1) k_ntt_dif<M><<<(m / 2 + 127) / 128, 128, 0, f.stream>>>(x, f.twi, m, len);
+}
+template <class M>
+void fft_dit(const FftState &f, uint32_t *x, uint32_t m) {    // bit-reversed in, natural out
+    for (uint32_t len = 2; len <= m && len; len <<= 1) k_ntt_dit<M><<<(m / 2 + 127) / 128, 128, 0, f.stream>>>(x, f.tw, m, len);
+}
+
+template <class M>
+int compute_h_impl(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out_host,
+                   const uint64_t **out_dev) {
+    const size_t m = d + 1;
+    int logm = 0;
+    while ((size_t(1) << logm) < m) ++logm;
+    if ((size_t(1) << logm) != m || logm > M::TWO_ADICITY || logm > 30)
+        return fail(ctx, B200MSM_ERR_ARG, "d + 1 = %zu is not a power of two within the field's 2-adicity (2^%d)", m, M::TWO_ADICITY);
+    int rc = fft_prepare<M>(ctx, logm);
+    if (rc) return rc;
+    FftState &f = ctx->fft;
+    cudaStream_t st = f.stream;
+    const size_t bytes = m * NLIMB * 4;
+    const unsigned gm = (unsigned)((m + 127) / 128), gm1 = (unsigned)((m + 1 + 127) / 128);
+    CU(cudaEventRecord(f.ev[0], st));
+    CU(cudaMemcpyAsync(f.a, ca, bytes, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(f.b, cb, bytes, cudaMemcpyDefault, st));
+    CU(cudaMemcpyAsync(f.c, cc, bytes, cudaMemcpyDefault, st));
+    for (uint32_t *x : {f.a, f.b, f.c}) {                       // coset evaluation of each of A, B, C
+        ifft_dif<M>(f, x, (uint32_t)m);
+        k_pointwise_mul<M><<<gm, 128, 0, st>>>(x, f.cg_br, (uint32_t)m);
+        fft_dit<M>(f, x, (uint32_t)m);
+    }
+    k_h_pointwise<M><<<gm, 128, 0, st>>>(f.a, f.b, f.c, f.consts + FC_Z_INV * NLIMB, (uint32_t)m);
+    ifft_dif<M>(f, f.a, (uint32_t)m);
+    k_h_final<M><<<gm1, 128, 0, st>>>(f.out, f.a, f.cgi_br, (uint32_t)m, logm);
+    if (out_host) CU(cudaMemcpyAsync(out_host, f.out, (m + 1) * NLIMB * 4, cudaMemcpyDefault, st));
+    CU(cudaEventRecord(f.ev[1], st));
+    CU(cudaGetLastError());
+    CU(cudaEventSynchronize(f.ev[1]));
+    CU(cudaEventElapsedTime(&f.last_ms, f.ev[0], f.ev[1]));
+    if (out_dev) *out_dev = reinterpret_cast<const uint64_t *>(f.out);
+    return B200MSM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200msm_compute_h(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out_host,
+                      const uint64_t **out_dev) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!ca || !cb || !cc || (!out_host && !out_dev)) return fail(ctx, B200MSM_ERR_ARG, "null pointer");
+    CU(cudaSetDevice(ctx->device));
+    // the scalar field of a curve is the base field of the other one
+    return ctx->curve == B200MSM_MNT4753 ? compute_h_impl<ModB>(ctx, d, ca, cb, cc, out_host, out_dev)
+                                         : compute_h_impl<ModA>(ctx, d, ca, cb, cc, out_host, out_dev);
+}
+
+int b200msm_compute_h_timings(b200msm_ctx *ctx, float ms[2]) {
+    if (!ctx || !ms) return B200MSM_ERR_ARG;
+    ms[0] = ctx->fft.last_ms;
+    ms[1] = ctx->fft.tables_ms;
+    return B200MSM_OK;
+}
+
+void b200msm_fft_release(b200msm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->fft.stream) cudaStreamSynchronize(ctx->fft.stream);
+    fft_free(ctx->fft);
+    if (ctx->fft.stream) {
+        cudaEventDestroy(ctx->fft.ev[0]);
+        cudaEventDestroy(ctx->fft.ev[1]);
+        cudaStreamDestroy(ctx->fft.stream);
+        ctx->fft.stream = nullptr;
+    }
+}
+
+}  // extern "C"

@@ -23,12 +23,18 @@ struct ModA {
     MSM_HD static constexpr uint32_t P(int j) { constexpr uint32_t t[NLIMB] = MNT753_MOD_A_U32; return t[j]; }
     MSM_HD static constexpr uint32_t R1(int j) { constexpr uint32_t t[NLIMB] = MNT753_R1_A_U32; return t[j]; }
     MSM_HD static constexpr uint32_t R2(int j) { constexpr uint32_t t[NLIMB] = MNT753_R2_A_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t ROOT(int j) { constexpr uint32_t t[NLIMB] = MNT753_ROOT_OF_UNITY_A_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t G17(int j) { constexpr uint32_t t[NLIMB] = MNT753_MONT17_A_U32; return t[j]; }
+    static constexpr int TWO_ADICITY = MNT753_TWO_ADICITY_A;
     static constexpr uint32_t INV = MNT753_INV_A_U32;
 };
 struct ModB {
     MSM_HD static constexpr uint32_t P(int j) { constexpr uint32_t t[NLIMB] = MNT753_MOD_B_U32; return t[j]; }
     MSM_HD static constexpr uint32_t R1(int j) { constexpr uint32_t t[NLIMB] = MNT753_R1_B_U32; return t[j]; }
     MSM_HD static constexpr uint32_t R2(int j) { constexpr uint32_t t[NLIMB] = MNT753_R2_B_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t ROOT(int j) { constexpr uint32_t t[NLIMB] = MNT753_ROOT_OF_UNITY_B_U32; return t[j]; }
+    MSM_HD static constexpr uint32_t G17(int j) { constexpr uint32_t t[NLIMB] = MNT753_MONT17_B_U32; return t[j]; }
+    static constexpr int TWO_ADICITY = MNT753_TWO_ADICITY_B;
     static constexpr uint32_t INV = MNT753_INV_B_U32;
 };
 

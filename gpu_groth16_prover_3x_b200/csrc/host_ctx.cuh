@@ -56,6 +56,16 @@ struct Lane {
     uint64_t info[8] = {};
 };
 
+// H-polynomial state (fft.cu): tables of the evaluation domain of size 2^logm and three work vectors
+struct FftState {
+    int logm = -1;
+    uint32_t *consts = nullptr, *tw = nullptr, *twi = nullptr, *cg_br = nullptr, *cgi_br = nullptr;
+    uint32_t *a = nullptr, *b = nullptr, *c = nullptr, *out = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {};
+    float last_ms = 0.f, tables_ms = 0.f;
+};
+
 struct b200msm_ctx {
     int curve = 0;
     int device = 0;
@@ -65,6 +75,7 @@ struct b200msm_ctx {
     size_t table_budget = size_t(32) << 30;  // bytes of window tables per base set (0: never build tables)
     std::vector<BaseSet> sets;
     Lane lanes[NLANES];
+    FftState fft;
     std::string err = "";
 };
 

@@ -194,6 +194,7 @@ int b200msm_create(int curve, int device, b200msm_ctx **out) {
 void b200msm_destroy(b200msm_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    b200msm_fft_release(ctx);
     for (int i = 0; i < NLANES; ++i) {
         Lane &ln = ctx->lanes[i];
         if (ln.stream) cudaStreamSynchronize(ln.stream);

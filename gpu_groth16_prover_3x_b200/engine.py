@@ -65,6 +65,10 @@ def load_library():
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
     lib.b200msm_set_table_budget.argtypes = [vp, sz]
     lib.b200msm_set_accumulator.argtypes = [vp, ci]
+    lib.b200msm_compute_h.argtypes = [vp, sz, vp, vp, vp, vp, ctypes.POINTER(vp)]
+    lib.b200msm_compute_h_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    lib.b200msm_fft_release.argtypes = [vp]
+    lib.b200msm_fft_release.restype = None
     lib.b200msm_bases_info.argtypes = [vp, ci, _u64p]
     lib.b200msm_last_timings.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), _u64p]
     lib.b200msm_microbench.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double)]
@@ -250,6 +254,20 @@ class MsmContext:
                  accumulate_launches=int(info[3]), kernel_launches=int(info[4]), bucket_sets=int(info[5]),
                  tables=int(info[6]), accumulator=int(info[7]))
         return d
+
+    def compute_h(self, ca, cb, cc, to_host=True):
+        """coefficients_for_H of the Groth16 prover (compute_H, cuda_prover_piecewise.cu:14-49) from the d + 1
+        evaluations ca, cb, cc (Montgomery Fr limbs, numpy or torch).  -> (uint64[(d + 2) * 12] or None, device pointer)."""
+        m = _nbytes(ca) // 96
+        out = np.zeros((m + 1) * 12, np.uint64) if to_host else None
+        dev = ctypes.c_void_p()
+        self._check(self.lib.b200msm_compute_h(self._h, m - 1, _ptr(ca), _ptr(cb), _ptr(cc), _ptr(out), ctypes.byref(dev)))
+        return out, dev.value
+
+    def compute_h_timings(self):
+        ms = (ctypes.c_float * 2)()
+        self._check(self.lib.b200msm_compute_h_timings(self._h, ms))
+        return {"compute_h_ms": float(ms[0]), "tables_ms": float(ms[1])}
 
     def set_accumulator(self, mode):
         """0: batched-affine rounds (default), 1: Jacobian mixed-addition chains."""

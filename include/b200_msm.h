@@ -95,6 +95,22 @@ int b200msm_to_affine(b200msm_ctx *ctx, int group, size_t n, const uint64_t *xyz
  * multi-GPU path; inside the reference the same fold is G - 1 libff additions after read_pt_*. */
 int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size_t n, uint64_t *out_xyz);
 
+/* The H-polynomial of the prover on the device: coefficients_for_H = compute_H(d, ca, cb, cc)
+ * (cuda_prover_piecewise.cu:14-49), i.e. the three inverse FFTs, three coset FFTs, the pointwise
+ * (ca * cb - cc) / Z and the inverse coset FFT that the reference runs on the CPU through libfqfft
+ * (basic_radix2_domain.tcc:63-126), over the scalar field Fr of the context's curve.  ca, cb, cc: d + 1
+ * Montgomery-form Fr elements each (host or device); d + 1 must be a power of two <= 2^s (s = 30 for
+ * MNT4753, 15 for MNT6753).  Result: d + 2 elements (the last one zero, like vector_Fr_zeros(m + 1)),
+ * copied to out_host when it is not NULL and left in device memory owned by the context -- *out_dev, valid
+ * until the next call -- so that the H-query MSM can take its scalars without a round trip over PCIe.
+ * Synchronous.  The domain tables (twiddles, coset powers: 3 (d+1) elements) are cached per size. */
+int b200msm_compute_h(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc,
+                      uint64_t *out_host, const uint64_t **out_dev);
+/* ms[0] = device time of the last b200msm_compute_h (copies included), ms[1] = one-off table build. */
+int b200msm_compute_h_timings(b200msm_ctx *ctx, float ms[2]);
+/* Free the FFT tables and work vectors (also done by b200msm_destroy). */
+void b200msm_fft_release(b200msm_ctx *ctx);
+
 /* Enqueue lane `lane` on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the
  * internal stream).  The reference hands a cudaStream_t& back to its caller for the same purpose
  * (reduce.cu:131-135): ordering the MSM against the caller's own work and timing it with events. */

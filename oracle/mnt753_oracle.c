@@ -660,3 +660,87 @@ int orc_fold_jacobian(int curve, int group, size_t n, const uint64_t *xyz, uint6
     wr_affine(G, out, &acc);
     return 0;
 }
+
+/* ---------------------------------------------------------------- H polynomial (compute_H)
+ * Restatement of compute_H<B> (cuda_prover_piecewise.cu:14-49) on libfqfft's basic_radix2_domain
+ * (depends/libfqfft/libfqfft/evaluation_domain/domains/basic_radix2_domain.tcc:63-126 and
+ * basic_radix2_domain_aux.tcc: _basic_serial_radix2_FFT = bit-reversal + Cooley-Tukey butterflies,
+ * _multiply_by_coset), over Fr of the curve. */
+static const uint64_t ROOT_A[NL] = MNT753_ROOT_OF_UNITY_A_U64, ROOT_B[NL] = MNT753_ROOT_OF_UNITY_B_U64;
+static const uint64_t GEN_A[NL] = MNT753_MONT17_A_U64, GEN_B[NL] = MNT753_MONT17_B_U64;
+
+static size_t bitreverse(size_t n, size_t l) {
+    size_t r = 0;
+    for (size_t k = 0; k < l; ++k) { r = (r << 1) | (n & 1); n >>= 1; }
+    return r;
+}
+/* basic_radix2_domain_aux.tcc:_basic_serial_radix2_FFT */
+static void serial_fft(const fpar *P, fp *a, size_t n, const fp *omega) {
+    const size_t logn = ff_log2(n);
+    for (size_t k = 0; k < n; ++k) {
+        const size_t rk = bitreverse(k, logn);
+        if (k < rk) { fp t = a[k]; a[k] = a[rk]; a[rk] = t; }
+    }
+    size_t m = 1;
+    for (size_t s = 1; s <= logn; ++s) {
+        fp w_m = *omega;                      /* omega^(n / 2m) by repeated squaring */
+        for (size_t e = n / (2 * m); e > 1; e >>= 1) fp_sqr(P, &w_m, &w_m);
+        for (size_t k = 0; k < n; k += 2 * m) {
+            fp w; fp_one(P, &w);
+            for (size_t j = 0; j < m; ++j) {
+                fp t, u = a[k + j];
+                fp_mul(P, &t, &w, &a[k + j + m]);
+                fp_add(P, &a[k + j], &u, &t);
+                fp_sub(P, &a[k + j + m], &u, &t);
+                fp_mul(P, &w, &w, &w_m);
+            }
+        }
+        m *= 2;
+    }
+}
+static void fft_scale(const fpar *P, fp *a, size_t n, const fp *c) { for (size_t i = 0; i < n; ++i) fp_mul(P, &a[i], &a[i], c); }
+/* _multiply_by_coset: a[i] *= g^i */
+static void mul_coset(const fpar *P, fp *a, size_t n, const fp *g) {
+    fp u = *g;
+    for (size_t i = 1; i < n; ++i) { fp_mul(P, &a[i], &a[i], &u); fp_mul(P, &u, &u, g); }
+}
+
+int orc_compute_h(int curve, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out) {
+    if (curve != 0 && curve != 1) return -1;
+    const fpar *P = curve == 0 ? &PAR_B : &PAR_A;          /* Fr of the curve */
+    const size_t s_adic = curve == 0 ? MNT753_TWO_ADICITY_B : MNT753_TWO_ADICITY_A;
+    const size_t m = d + 1, logm = ff_log2(m);
+    if (((size_t)1 << logm) != m || logm > s_adic) return -2;
+    fp omega, omega_inv, g, g_inv, m_inv, z_inv, one;
+    memcpy(omega.l, curve == 0 ? ROOT_B : ROOT_A, 96);
+    memcpy(g.l, curve == 0 ? GEN_B : GEN_A, 96);
+    fp_one(P, &one);
+    for (size_t i = logm; i < s_adic; ++i) fp_sqr(P, &omega, &omega);     /* get_root_of_unity(m) */
+    fp_inv(P, &omega_inv, &omega);
+    fp_inv(P, &g_inv, &g);
+    { uint64_t mi[NL] = {0}; mi[logm / 64] = (uint64_t)1 << (logm % 64); fp mm; fp_to_mont(P, &mm, mi); fp_inv(P, &m_inv, &mm); }
+    { fp z = g; for (size_t i = 0; i < logm; ++i) fp_sqr(P, &z, &z); fp_sub(P, &z, &z, &one); fp_inv(P, &z_inv, &z); }
+    fp *A = malloc(m * sizeof(fp)), *B = malloc(m * sizeof(fp)), *C = malloc(m * sizeof(fp));
+    if (!A || !B || !C) { free(A); free(B); free(C); return -3; }
+    memcpy(A, ca, m * 96); memcpy(B, cb, m * 96); memcpy(C, cc, m * 96);
+    fp *v[3] = {A, B, C};
+    for (int k = 0; k < 3; ++k) {                           /* iFFT then cosetFFT of each */
+        serial_fft(P, v[k], m, &omega_inv);
+        fft_scale(P, v[k], m, &m_inv);
+        mul_coset(P, v[k], m, &g);
+        serial_fft(P, v[k], m, &omega);
+    }
+    for (size_t i = 0; i < m; ++i) {                        /* H_tmp = (ca * cb - cc) / Z(g) */
+        fp_mul(P, &A[i], &A[i], &B[i]);
+        fp_sub(P, &A[i], &A[i], &C[i]);
+        fp_mul(P, &A[i], &A[i], &z_inv);
+    }
+    serial_fft(P, A, m, &omega_inv);                        /* icosetFFT */
+    fft_scale(P, A, m, &m_inv);
+    mul_coset(P, A, m, &g_inv);
+    memcpy(out, A, m * 96);
+    memset(out + m * NL, 0, 96);                            /* vector_Fr_zeros(m + 1) */
+    free(A); free(B); free(C);
+    return 0;
+}
+

@@ -51,6 +51,10 @@ int orc_jacobian_to_affine(int curve, int group, const uint64_t *xyz, uint64_t *
 /* sum of n Jacobian partials (multi-GPU host fold), result affine. */
 int orc_fold_jacobian(int curve, int group, size_t n, const uint64_t *xyz, uint64_t *out);
 
+/* coefficients_for_H = compute_H(d, ca, cb, cc) (cuda_prover_piecewise.cu:14-49) over Fr: ca, cb, cc hold
+ * d + 1 Montgomery elements each (d + 1 a power of two), out receives d + 2 (the last one zero). */
+int orc_compute_h(int curve, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out);
+
 int orc_num_threads(void);
 void orc_set_num_threads(int t);
 

@@ -92,6 +92,7 @@ class CpuLib:
         f("fr_to_mont").argtypes = [ctypes.c_int, ctypes.c_size_t, _u64p, _u64p]
         f("jacobian_to_affine").argtypes = [ctypes.c_int, ctypes.c_int, _u64p, _u64p]
         f("set_num_threads").argtypes = [ctypes.c_int]
+        f("compute_h").argtypes = [ctypes.c_int, ctypes.c_size_t, _u64p, _u64p, _u64p, _u64p]
         if prefix == "orc":
             f("gen_bases").argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, _u64p, _u64p, _u64p]
             f("msm_closed_form").argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, _u64p, _u64p, _u64p, _u64p]
@@ -140,6 +141,15 @@ class CpuLib:
         t = self._f("msm")(curve, group, n, _p(bases), _p(scalars), _p(out), method, chunks, prefilter)
         assert t >= 0
         return out, t
+
+    def compute_h(self, curve, ca, cb, cc):
+        """coefficients_for_H (compute_H, cuda_prover_piecewise.cu:14-49): d + 1 evaluations each -> d + 2 coefficients."""
+        m = ca.size // 12
+        out = np.zeros((m + 1) * 12, np.uint64)
+        rc = self._f("compute_h")(curve, m - 1, _p(np.ascontiguousarray(ca)), _p(np.ascontiguousarray(cb)),
+                                  _p(np.ascontiguousarray(cc)), _p(out))
+        assert rc == 0, rc
+        return out
 
     def jacobian_to_affine(self, curve, group, xyz):
         out = np.zeros(24 * degree(curve, group), np.uint64)

@@ -27,6 +27,7 @@
 #include <libff/algebra/scalar_multiplication/multiexp.hpp>
 #include <libff/common/profiling.hpp>
 #include <libff/common/rng.hpp>
+#include <libfqfft/evaluation_domain/get_evaluation_domain.hpp>
 
 using namespace libff;
 
@@ -353,3 +354,40 @@ int ref_jacobian_to_affine(int curve, int group, const uint64_t *xyz, uint64_t *
 }
 
 }  // extern "C"
+
+// compute_H exactly as the reference's GPU prover driver does it (cuda_prover_piecewise.cu:14-49), through
+// libfqfft's own domain object (prover_reference_functions.cpp: domain_iFFT / domain_cosetFFT / ...).
+namespace {
+template <typename ppT>
+int compute_h_ref(size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out) {
+    typedef Fr<ppT> F;
+    const size_t m = d + 1;
+    std::vector<F> A(m), B(m), C(m);
+    for (size_t i = 0; i < m; ++i) {
+        const uint64_t *p = ca + i * L; A[i] = rd_fp<F>(p);
+        p = cb + i * L; B[i] = rd_fp<F>(p);
+        p = cc + i * L; C[i] = rd_fp<F>(p);
+    }
+    auto domain = libfqfft::get_evaluation_domain<F>(d + 1);
+    if (domain->m != m) return -2;
+    domain->iFFT(A);
+    domain->iFFT(B);
+    domain->cosetFFT(A, F::multiplicative_generator);
+    domain->cosetFFT(B, F::multiplicative_generator);
+    for (size_t i = 0; i < m; ++i) A[i] *= B[i];
+    domain->iFFT(C);
+    domain->cosetFFT(C, F::multiplicative_generator);
+    for (size_t i = 0; i < m; ++i) A[i] -= C[i];
+    domain->divide_by_Z_on_coset(A);
+    domain->icosetFFT(A, F::multiplicative_generator);
+    for (size_t i = 0; i < m; ++i) { uint64_t *o = out + i * L; wr_fp(o, A[i]); }
+    memset(out + m * L, 0, L * 8);
+    return 0;
+}
+}  // namespace
+
+extern "C" int ref_compute_h(int curve, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out) {
+    ref_init();
+    return curve == 0 ? compute_h_ref<mnt4753_pp>(d, ca, cb, cc, out) : compute_h_ref<mnt6753_pp>(d, ca, cb, cc, out);
+}
+

@@ -44,7 +44,7 @@ def oracle():
 @pytest.fixture(scope="session")
 def golden():
     return {name: np.load(os.path.join(GOLD, name + ".npz")) for name in
-            ("field_vectors", "point_vectors", "msm_vectors", "generators")}
+            ("field_vectors", "point_vectors", "msm_vectors", "generators", "h_vectors")}
 
 
 @pytest.fixture(scope="session")

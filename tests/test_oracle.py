@@ -85,3 +85,13 @@ def test_scalar_generator_matches_fixture(golden):
     for c in (0, 1):
         mine = po.gen_scalars(c, 10, 11)
         assert (mine == z["c%d_g1_scalars" % c][:120]).all()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_compute_h_restatement_matches_reference_fixtures(oracle, golden, curve):
+    """orc_compute_h (radix-2 FFTs restated from libfqfft) against compute_H run through the reference's own
+    libfqfft domain (tools/gen_golden.py -> tests/golden/h_vectors.npz)."""
+    z = golden["h_vectors"]
+    for m in (2, 8, 64, 512):
+        k = "c%d_m%d_" % (curve, m)
+        assert (oracle.compute_h(curve, z[k + "ca"], z[k + "cb"], z[k + "cc"]) == z[k + "out"]).all(), m

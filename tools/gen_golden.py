@@ -170,3 +170,15 @@ np.savez_compressed(os.path.join(GOLD, "msm_vectors.npz"), **msm)
 print("golden fixtures written to", GOLD)
 for f in sorted(os.listdir(GOLD)):
     print("  %-24s %8d B" % (f, os.path.getsize(os.path.join(GOLD, f))))
+
+# ---- H polynomial: compute_H of the reference (libfqfft through libref.so) on seeded inputs ---------------------
+hv = {}
+for curve in (0, 1):
+    for logm in (1, 3, 6, 9):
+        m = 1 << logm
+        ca, cb, cc = (po.gen_scalars(curve, m, 900 + 10 * logm + k) for k in range(3))
+        hv["c%d_m%d_ca" % (curve, m)], hv["c%d_m%d_cb" % (curve, m)], hv["c%d_m%d_cc" % (curve, m)] = ca, cb, cc
+        hv["c%d_m%d_out" % (curve, m)] = ref.compute_h(curve, ca, cb, cc)
+np.savez_compressed(os.path.join(GOLD, "h_vectors.npz"), **hv)
+print("wrote h_vectors.npz")
+
