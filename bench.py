@@ -331,6 +331,11 @@ def run_b200(args):
         line["fold_ms"] = fold_ms
     if world == 1 and not args.no_secondary and (curve, group) == (0, 1):
         line["secondary"] = secondary_workload(args, local)
+    if world == 1 and not args.no_cpu and not args.no_secondary:
+        try:
+            line["proof_latency"] = proof_latency()
+        except Exception as e:  # the headline line must not depend on the optional leg
+            line["proof_latency"] = {"error": str(e)[:200]}
     emit(line)
     ctx.close()
     if world > 1:
@@ -374,6 +379,45 @@ def secondary_workload(args, device):
                 "phases_ms": {k: t[k] for k in pkg.MsmContext.PHASES}}
     finally:
         ctx.close()
+
+
+def proof_latency():
+    """BASELINE.json's second headline, end-to-end proof latency, on the reference's `generate_parameters fast`
+    instance (MNT4753 d = 2^14 - 1, MNT6753 d = 2^10 - 1; the default 2^20 instance takes ~10 minutes of CPU to
+    generate, see tools/full_proof.sh and DESIGN.md for that run).  Reference arm: the reference's own CPU prover
+    `main <curve> compute`; ours: its prover driver with the five MSMs and the H polynomial on the engine
+    (tests/integration/b200_prover.cpp), third proof of a resident process.  Both come from oracle/_ref (test
+    infrastructure, built where /root/reference exists); returns None when they are not there."""
+    import hashlib
+    import re
+    import tempfile
+    ref = os.path.join(ROOT, "oracle", "_ref")
+    bins = [os.path.join(ref, b) for b in ("generate_parameters", "main", "b200_prover")]
+    if not all(os.path.exists(b) for b in bins):
+        return None
+    out = {"instance": "generate_parameters fast", "curves": {}}
+    with tempfile.TemporaryDirectory() as d:
+        subprocess.run([bins[0], "fast"], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=900)
+        for curve in ("MNT4753", "MNT6753"):
+            prm, inp = curve + "-parameters", curve + "-input"
+            t0 = time.perf_counter()
+            log = subprocess.run([bins[1], curve, "compute", prm, inp, "out-ref"], cwd=d, check=True, capture_output=True,
+                                 text=True, timeout=1800).stdout
+            t_ref_wall = time.perf_counter() - t0
+            log2 = subprocess.run([bins[2], curve, "compute", prm, inp, "out-b200", "1", "gpu-h", "3"], cwd=d, check=True,
+                                  capture_output=True, text=True, timeout=900).stdout
+            ours = [float(x) for x in re.findall(r"Total time from input to output: ([0-9.]+) ms", log2)]
+            total = re.findall(r"Total runtime \(incl. file reads, uploads\): ([0-9.]+) ms", log2)
+            upload = re.findall(r"upload \+ window tables: ([0-9.]+) ms", log2)
+            same = hashlib.sha256(open(os.path.join(d, "out-ref"), "rb").read()).digest() == \
+                hashlib.sha256(open(os.path.join(d, "out-b200"), "rb").read()).digest()
+            out["curves"][curve] = {"b200_input_to_proof_s": ours[-1] / 1e3 if ours else None,
+                                    "b200_first_proof_s": ours[0] / 1e3 if ours else None,
+                                    "b200_key_upload_and_tables_s": float(upload[0]) / 1e3 if upload else None,
+                                    "b200_process_total_3_proofs_s": float(total[0]) / 1e3 if total else None,
+                                    "reference_cpu_process_wall_s": t_ref_wall,
+                                    "proof_sha256_equal": bool(same)}
+    return out
 
 
 _REAL_STDOUT = None

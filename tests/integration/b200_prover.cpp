@@ -9,7 +9,11 @@
 // handles are opaque outside it (prover_reference_include/prover_reference_functions.hpp:9-28) and the
 // H-query scalars produced by compute_H must be handed to the engine as raw limbs.
 //
-//   b200_prover <MNT4753|MNT6753> compute <params> <input> <output> [n_gpus]
+//   b200_prover <MNT4753|MNT6753> compute <params> <input> <output> [n_gpus] [cpu-h|gpu-h] [repeats]
+//
+// By default the H polynomial is computed on the device too (b200msm_compute_h) and its
+// coefficients never leave HBM before the H-query MSM; `cpu-h` keeps the reference's libfqfft path
+// (compute_H, cuda_prover_piecewise.cu:14-49) for comparison.
 //
 // mirrors `cuda_prover_piecewise <curve> compute <params> <input> <output>` (cuda_prover_piecewise.cu:232-263)
 // minus the preprocessed-table argument, which no longer exists.  tests/test_gpu_prover.py checks that the
@@ -85,7 +89,7 @@ struct Query {
 };
 
 template <class B>
-int run(const char *params_path, const char *input_path, const char *output_path, int n_gpus) {
+int run(const char *params_path, const char *input_path, const char *output_path, int n_gpus, bool cpu_h, int repeats) {
     typedef CurveOf<B> C;
     B::init_public_params();
     auto t_all = Clock::now();
@@ -123,6 +127,7 @@ int run(const char *params_path, const char *input_path, const char *output_path
     }
     printf("upload + window tables: %.1f ms\n", ms_since(t));
 
+  for (int rep = 0; rep < repeats; ++rep) {   // a resident prover: later proofs reuse contexts, tables and arenas
     auto t_main = Clock::now();
     std::vector<char> ifile = slurp(input_path);
     const uint64_t *w = (const uint64_t *)ifile.data();  // w[0..m] Fr, Montgomery limbs (main.cpp:35-85)
@@ -149,11 +154,25 @@ int run(const char *params_path, const char *input_path, const char *output_path
     launch(1, 1, w);                                    // B1
     launch(2, 2, w);                                    // B2 (G2)
     launch(3, 3, w + (primary_input_size + 1) * 12);    // L:  w[2..m]   (cuda_prover_piecewise.cu:167)
-    // CPU work overlaps the four MSMs, as in the reference (cuda_prover_piecewise.cu:174-179)
-    auto coefficients_for_H = compute_H<B>(d, B::input_ca(inputs), B::input_cb(inputs), B::input_cc(inputs));
-    printf("compute_H (CPU, libfqfft): %.1f ms\n", ms_since(t_gpu));
+    const uint64_t *h_scalars = nullptr;
+    std::vector<uint64_t> h_copy;
+    if (cpu_h) {
+        // CPU work overlaps the four MSMs, as in the reference (cuda_prover_piecewise.cu:174-179)
+        auto coefficients_for_H = compute_H<B>(d, B::input_ca(inputs), B::input_cb(inputs), B::input_cc(inputs));
+        printf("compute_H (CPU, libfqfft): %.1f ms\n", ms_since(t_gpu));
+        h_scalars = (const uint64_t *)(coefficients_for_H->data->data() + coefficients_for_H->offset);
+    } else {
+        // ca, cb, cc follow w in the input file (main.cpp:35-85): d + 1 Fr elements each
+        const uint64_t *ca = w + (m + 1) * 12, *cb = ca + (d + 1) * 12, *cc = cb + (d + 1) * 12;
+        auto t_h = Clock::now();
+        const uint64_t *h_dev = nullptr;
+        CHECK(ctx[0], b200msm_compute_h(ctx[0], d, ca, cb, cc, n_gpus > 1 ? (h_copy.resize((d + 2) * 12), h_copy.data()) : nullptr, &h_dev));
+        float hms[2];
+        b200msm_compute_h_timings(ctx[0], hms);
+        printf("compute_H (device): %.1f ms wall, %.2f ms device, domain tables %.2f ms\n", ms_since(t_h), hms[0], hms[1]);
+        h_scalars = n_gpus > 1 ? h_copy.data() : h_dev;   // one GPU: the coefficients stay in HBM
+    }
     finish(0, 0);
-    const uint64_t *h_scalars = (const uint64_t *)(coefficients_for_H->data->data() + coefficients_for_H->offset);
     launch(4, 0, h_scalars);                            // H:  d coefficients
     finish(1, 1);
     finish(2, 2);
@@ -171,6 +190,10 @@ int run(const char *params_path, const char *input_path, const char *output_path
     auto final_C = B::G1_add(evaluation_Ht, Lt1_plus_scaled_Bt1);
     B::groth16_output_write(evaluation_At, evaluation_Bt2, final_C, output_path);
     printf("Total time from input to output: %.1f ms\n", ms_since(t_main));
+    B::delete_G1(evaluation_At); B::delete_G1(evaluation_Bt1); B::delete_G2(evaluation_Bt2); B::delete_G1(evaluation_Lt);
+    B::delete_G1(evaluation_Ht); B::delete_G1(scaled_Bt1); B::delete_G1(Lt1_plus_scaled_Bt1); B::delete_G1(final_C);
+    B::delete_groth16_input(inputs);
+  }
     printf("Total runtime (incl. file reads, uploads): %.1f ms\n", ms_since(t_all));
     for (auto c : ctx) b200msm_destroy(c);
     return 0;
@@ -181,13 +204,15 @@ int run(const char *params_path, const char *input_path, const char *output_path
 int main(int argc, char **argv) {
     setbuf(stdout, NULL);
     if (argc < 6 || std::string(argv[2]) != "compute") {
-        fprintf(stderr, "usage: %s <MNT4753|MNT6753> compute <params> <input> <output> [n_gpus]\n", argv[0]);
+        fprintf(stderr, "usage: %s <MNT4753|MNT6753> compute <params> <input> <output> [n_gpus] [cpu-h|gpu-h] [repeats]\n", argv[0]);
         return 1;
     }
     const int n_gpus = argc > 6 ? atoi(argv[6]) : 1;
+    const bool cpu_h = argc > 7 && std::string(argv[7]) == "cpu-h";
+    const int repeats = argc > 8 ? atoi(argv[8]) : 1;
     const std::string curve(argv[1]);
-    if (curve == "MNT4753") return run<mnt4753_libsnark>(argv[3], argv[4], argv[5], n_gpus);
-    if (curve == "MNT6753") return run<mnt6753_libsnark>(argv[3], argv[4], argv[5], n_gpus);
+    if (curve == "MNT4753") return run<mnt4753_libsnark>(argv[3], argv[4], argv[5], n_gpus, cpu_h, repeats);
+    if (curve == "MNT6753") return run<mnt6753_libsnark>(argv[3], argv[4], argv[5], n_gpus, cpu_h, repeats);
     fprintf(stderr, "unknown curve %s\n", argv[1]);
     return 1;
 }

@@ -31,13 +31,18 @@ def fast_params(tmp_path_factory):
 
 @pytest.mark.parametrize("curve", ["MNT4753", "MNT6753"])
 def test_proof_sha256_equals_reference_cpu_prover(fast_params, curve):
+    """MSMs and the H polynomial on the device (default), then the same with the reference's CPU FFTs."""
     d = fast_params
     params, inp = "%s-parameters" % curve, "%s-input" % curve
-    subprocess.run([BINS[1], curve, "compute", params, inp, curve + "-output-ref"], cwd=d, check=True,
-                   stdout=subprocess.DEVNULL, timeout=1800)
-    out = subprocess.run([BINS[2], curve, "compute", params, inp, curve + "-output-b200"], cwd=d, check=True,
-                         capture_output=True, text=True, timeout=900).stdout
-    print(out)
-    a, b = os.path.join(d, curve + "-output-ref"), os.path.join(d, curve + "-output-b200")
-    assert os.path.getsize(a) == os.path.getsize(b) == (768 if curve == "MNT4753" else 960)
-    assert sha256(a) == sha256(b)
+    ref_out = os.path.join(d, curve + "-output-ref")
+    if not os.path.exists(ref_out):
+        subprocess.run([BINS[1], curve, "compute", params, inp, curve + "-output-ref"], cwd=d, check=True,
+                       stdout=subprocess.DEVNULL, timeout=1800)
+    for extra in ([], ["1", "cpu-h"]):
+        name = curve + "-output-b200" + ("-cpuh" if extra else "")
+        out = subprocess.run([BINS[2], curve, "compute", params, inp, name] + extra, cwd=d, check=True,
+                             capture_output=True, text=True, timeout=900).stdout
+        print(out)
+        b = os.path.join(d, name)
+        assert os.path.getsize(ref_out) == os.path.getsize(b) == (768 if curve == "MNT4753" else 960)
+        assert sha256(ref_out) == sha256(b), extra
