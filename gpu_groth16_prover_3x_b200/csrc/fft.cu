@@ -2,6 +2,8 @@
 // Replaces compute_H<B> (cuda_prover_piecewise.cu:14-49), i.e. B::domain_iFFT / domain_cosetFFT /
 // vector_Fr_muleq / vector_Fr_subeq / domain_divide_by_Z_on_coset / domain_icosetFFT
 // (prover_reference_functions.cpp) on libfqfft's basic_radix2_domain.
+#include <cstdlib>
+
 #include "host_ctx.cuh"
 #include "fft_kernels.cuh"
 
@@ -25,6 +27,8 @@ int fft_prepare(b200msm_ctx *ctx, int logm) {
     }
     if (f.logm == logm) return B200MSM_OK;
     fft_free(f);
+    CU(cudaFuncSetAttribute(k_ntt_tile<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << NTT_TILE_BITS));
+    CU(cudaFuncSetAttribute(k_ntt_tile<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << NTT_TILE_BITS));
     const size_t m = size_t(1) << logm, EB = NLIMB * 4;
     CU(cudaMalloc(&f.consts, FC_COUNT * EB));
     CU(cudaMalloc(&f.tw, std::max<size_t>(m / 2, 1) * EB));
@@ -54,12 +58,34 @@ int fft_prepare(b200msm_ctx *ctx, int logm) {
     return B200MSM_OK;
 }
 
+
+
+// bits of the index are processed in groups of up to NTT_TILE_BITS by k_ntt_tile; transforms of fewer than
+// 2^6 points (and the B200MSM_FFT_SIMPLE=1 debugging switch) use the one-launch-per-stage kernels
+bool fft_simple() {
+    static const bool s = getenv("B200MSM_FFT_SIMPLE") != nullptr;
+    return s;
+}
+template <class M, bool DIF>
+void ntt_tiled(const FftState &f, uint32_t *x, int logm, const uint32_t *tw) {
+    // DIF: highest bits first; DIT: lowest bits first.  Groups of equal size, at most NTT_TILE_BITS each.
+    const int ngroups = (logm + NTT_TILE_BITS - 1) / NTT_TILE_BITS;
+    int bits[8], start[8];
+    for (int g = 0, s = 0; g < ngroups; ++g) { bits[g] = logm / ngroups + (g < logm % ngroups ? 1 : 0); start[g] = s; s += bits[g]; }
+    for (int k = 0; k < ngroups; ++k) {
+        const int g = DIF ? ngroups - 1 - k : k;
+        const size_t smem = (size_t(96) << bits[g]);
+        k_ntt_tile<M, DIF><<<1u << (logm - bits[g]), NTT_TILE_THREADS, smem, f.stream>>>(x, tw, logm, start[g], bits[g]);
+    }
+}
 template <class M>
-void ifft_dif(const FftState &f, uint32_t *x, uint32_t m) {   // natural in, bit-reversed out, NOT yet scaled by 1/m
+void ifft_dif(const FftState &f, uint32_t *x, uint32_t m, int logm) {   // natural in, bit-reversed out, NOT yet scaled by 1/m
+    if (logm >= 6 && !fft_simple()) { ntt_tiled<M, true>(f, x, logm, f.twi); return; }
     for (uint32_t len = m; len >= 2; len >>= 1) k_ntt_dif<M><<<(m / 2 + 127) / 128, 128, 0, f.stream>>>(x, f.twi, m, len);
 }
 template <class M>
-void fft_dit(const FftState &f, uint32_t *x, uint32_t m) {    // bit-reversed in, natural out
+void fft_dit(const FftState &f, uint32_t *x, uint32_t m, int logm) {    // bit-reversed in, natural out
+    if (logm >= 6 && !fft_simple()) { ntt_tiled<M, false>(f, x, logm, f.tw); return; }
     for (uint32_t len = 2; len <= m && len; len <<= 1) k_ntt_dit<M><<<(m / 2 + 127) / 128, 128, 0, f.stream>>>(x, f.tw, m, len);
 }
 
@@ -82,12 +108,12 @@ int compute_h_impl(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_
     CU(cudaMemcpyAsync(f.b, cb, bytes, cudaMemcpyDefault, st));
     CU(cudaMemcpyAsync(f.c, cc, bytes, cudaMemcpyDefault, st));
     for (uint32_t *x : {f.a, f.b, f.c}) {                       // coset evaluation of each of A, B, C
-        ifft_dif<M>(f, x, (uint32_t)m);
+        ifft_dif<M>(f, x, (uint32_t)m, logm);
         k_pointwise_mul<M><<<gm, 128, 0, st>>>(x, f.cg_br, (uint32_t)m);
-        fft_dit<M>(f, x, (uint32_t)m);
+        fft_dit<M>(f, x, (uint32_t)m, logm);
     }
     k_h_pointwise<M><<<gm, 128, 0, st>>>(f.a, f.b, f.c, f.consts + FC_Z_INV * NLIMB, (uint32_t)m);
-    ifft_dif<M>(f, f.a, (uint32_t)m);
+    ifft_dif<M>(f, f.a, (uint32_t)m, logm);
     k_h_final<M><<<gm1, 128, 0, st>>>(f.out, f.a, f.cgi_br, (uint32_t)m, logm);
     if (out_host) CU(cudaMemcpyAsync(out_host, f.out, (m + 1) * NLIMB * 4, cudaMemcpyDefault, st));
     CU(cudaEventRecord(f.ev[1], st));

@@ -115,6 +115,68 @@ __global__ void __launch_bounds__(128) k_ntt_dit(uint32_t *a, const uint32_t *tw
     st_fq(pv, d);
 }
 
+
+// ---- several stages per pass ---------------------------------------------------------------------------
+// A block owns a TILE of T = 2^nbits elements whose indices differ only in bits [sbit, sbit + nbits) and runs
+// all butterflies on those bits in shared memory: a 2^20-point transform is two passes over HBM instead of
+// twenty.  Tile element u lives at global index  base + (u << sbit); in shared memory its 128-bit quad q sits
+// at sm[q * T + u], so that neighbouring threads touch neighbouring 16-byte words (no bank conflicts).
+// DIF runs the tile's bits from the highest down, DIT from the lowest up; the twiddle of the butterfly on
+// global bit b with lower index bits j is w^(j << (logn - b - 1)), looked up in the full table (L2 resident).
+constexpr int NTT_TILE_THREADS = 256;
+constexpr int NTT_TILE_BITS = 10;   // at most 1024 elements = 96 KB of shared memory per block
+
+template <class M, bool DIF>
+__global__ void __launch_bounds__(NTT_TILE_THREADS) k_ntt_tile(uint32_t *a, const uint32_t *tw, int logn, int sbit, int nbits) {
+    extern __shared__ uint4 sm[];
+    const uint32_t T = 1u << nbits;
+    const uint32_t o = blockIdx.x;
+    const uint32_t lo = o & ((1u << sbit) - 1u), hi = o >> sbit;
+    const size_t base = ((size_t)hi << (sbit + nbits)) | lo;
+    for (uint32_t u = threadIdx.x; u < T; u += blockDim.x) {
+        const uint4 *g = reinterpret_cast<const uint4 *>(a + (base + ((size_t)u << sbit)) * NLIMB);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) sm[q * T + u] = g[q];
+    }
+    __syncthreads();
+    for (int step = 0; step < nbits; ++step) {
+        const int lb = DIF ? nbits - 1 - step : step;
+        const uint32_t h = 1u << lb;
+        const int b = sbit + lb;
+        for (uint32_t t = threadIdx.x; t < T / 2; t += blockDim.x) {
+            const uint32_t jl = t & (h - 1u), u0 = ((t >> lb) << (lb + 1)) | jl, u1 = u0 + h;
+            fq_t x, y, sres, dres;
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                uint4 v = sm[q * T + u0]; x[4 * q] = v.x; x[4 * q + 1] = v.y; x[4 * q + 2] = v.z; x[4 * q + 3] = v.w;
+                v = sm[q * T + u1]; y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w;
+            }
+            const size_t j = ((size_t)jl << sbit) | lo;
+            const size_t e = j << (logn - b - 1);
+            if (DIF) {
+                fq_add<M>(sres, x, y);
+                fq_sub<M>(dres, x, y);
+                if (e) { fq_t w; ld_fq(w, tw + e * NLIMB); fq_mul<M>(dres, dres, w); }
+            } else {
+                if (e) { fq_t w; ld_fq(w, tw + e * NLIMB); fq_mul<M>(y, y, w); }
+                fq_add<M>(sres, x, y);
+                fq_sub<M>(dres, x, y);
+            }
+#pragma unroll
+            for (int q = 0; q < 6; ++q) {
+                uint4 v; v.x = sres[4 * q]; v.y = sres[4 * q + 1]; v.z = sres[4 * q + 2]; v.w = sres[4 * q + 3]; sm[q * T + u0] = v;
+                v.x = dres[4 * q]; v.y = dres[4 * q + 1]; v.z = dres[4 * q + 2]; v.w = dres[4 * q + 3]; sm[q * T + u1] = v;
+            }
+        }
+        __syncthreads();
+    }
+    for (uint32_t u = threadIdx.x; u < T; u += blockDim.x) {
+        uint4 *g = reinterpret_cast<uint4 *>(a + (base + ((size_t)u << sbit)) * NLIMB);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) g[q] = sm[q * T + u];
+    }
+}
+
 // a[i] *= tab[i]
 template <class M>
 __global__ void __launch_bounds__(128) k_pointwise_mul(uint32_t *a, const uint32_t *tab, uint32_t n) {

@@ -363,6 +363,28 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     if (!ctx) return B200MSM_ERR_ARG;
     if (!gops || iters <= 0 || kind < 0 || kind > 18) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
+    if (kind >= 15) {  // register multiplier at 4 (kind 15), 8 (16) or 12 (17) warps per SM: does ONE warp per scheduler fill the pipe?
+        if (kind > 17) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+        uint32_t *dd = nullptr;
+        CU(cudaMalloc(&dd, 256));
+        cudaEvent_t a0, a1;
+        CU(cudaEventCreate(&a0));
+        CU(cudaEventCreate(&a1));
+        const int nb = ctx->sm_count * (kind - 14);
+        for (int rep = 0; rep < 2; ++rep) {
+            CU(cudaEventRecord(a0, 0));
+            k_mb_fqmul<ModA, false><<<nb, 128>>>(dd, iters);
+            CU(cudaEventRecord(a1, 0));
+            CU(cudaEventSynchronize(a1));
+        }
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, a0, a1));
+        cudaEventDestroy(a0);
+        cudaEventDestroy(a1);
+        cudaFree(dd);
+        *gops = double(nb) * 128 * iters / (double(ms) * 1e6);
+        return B200MSM_OK;
+    }
     if (kind >= 7) {  // slab multiplier: kind = 7 + 4 * (group - 1) + (blocks per SM - 1), blocks per SM in 1..4
         const int group = kind < 11 ? B200MSM_G1 : B200MSM_G2, bps = (kind - 7) % 4 + 1;
         if (kind > 14) return fail(ctx, B200MSM_ERR_ARG, "bad argument");

@@ -144,7 +144,8 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
  *           fq_inv, the plain binary gcd, the approximation-based fast path alone (fails if it ever needs
  *           the fallback);
  *       7..10 (G1) / 11..14 (G2) = the slab multiplier Team::mul (operands in shared memory, as used by
- *           every curve operation) with 1..4 resident blocks per SM; returns 10^9 tower products/s. */
+ *           every curve operation) with 1..4 resident blocks per SM; returns 10^9 tower products/s;
+ *       15, 16, 17 = kind 2 (register operands) with only 4, 8, 12 warps per SM. */
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops);
 
 /* Self-test hooks (used by tests/ only): the device field / point layer applied elementwise.
