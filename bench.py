@@ -383,16 +383,17 @@ def secondary_workload(args, device):
 
 def proof_latency():
     """BASELINE.json's second headline, end-to-end proof latency, on the reference's `generate_parameters fast`
-    instance (MNT4753 d = 2^14 - 1, MNT6753 d = 2^10 - 1; the default 2^20 instance takes ~10 minutes of CPU to
+    instance (MNT4753 d = 2^14 - 1, MNT6753 d = 2^10 - 1; the default 2^20 instance takes minutes of CPU to
     generate, see tools/full_proof.sh and DESIGN.md for that run).  Reference arm: the reference's own CPU prover
-    `main <curve> compute`; ours: its prover driver with the five MSMs and the H polynomial on the engine
-    (tests/integration/b200_prover.cpp), third proof of a resident process.  Both come from oracle/_ref (test
-    infrastructure, built where /root/reference exists); returns None when they are not there."""
+    `main <curve> compute` (oracle/_ref, test infrastructure built where /root/reference exists); ours: the
+    product's command-line prover b200_prove (b200msm_key_load_file + b200msm_prove), third proof of a resident
+    process.  Returns None when the reference binaries are not there."""
     import hashlib
     import re
     import tempfile
     ref = os.path.join(ROOT, "oracle", "_ref")
-    bins = [os.path.join(ref, b) for b in ("generate_parameters", "main", "b200_prover")]
+    bins = [os.path.join(ref, "generate_parameters"), os.path.join(ref, "main"),
+            os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "b200_prove")]
     if not all(os.path.exists(b) for b in bins):
         return None
     out = {"instance": "generate_parameters fast", "curves": {}}
@@ -404,11 +405,11 @@ def proof_latency():
             log = subprocess.run([bins[1], curve, "compute", prm, inp, "out-ref"], cwd=d, check=True, capture_output=True,
                                  text=True, timeout=1800).stdout
             t_ref_wall = time.perf_counter() - t0
-            log2 = subprocess.run([bins[2], curve, "compute", prm, inp, "out-b200", "1", "gpu-h", "3"], cwd=d, check=True,
+            log2 = subprocess.run([bins[2], curve, "compute", prm, inp, "out-b200", "3"], cwd=d, check=True,
                                   capture_output=True, text=True, timeout=900).stdout
             ours = [float(x) for x in re.findall(r"Total time from input to output: ([0-9.]+) ms", log2)]
-            total = re.findall(r"Total runtime \(incl. file reads, uploads\): ([0-9.]+) ms", log2)
-            upload = re.findall(r"upload \+ window tables: ([0-9.]+) ms", log2)
+            total = re.findall(r"Total runtime \(incl. key load\): ([0-9.]+) ms", log2)
+            upload = re.findall(r"key load \+ window tables: ([0-9.]+) ms", log2)
             same = hashlib.sha256(open(os.path.join(d, "out-ref"), "rb").read()).digest() == \
                 hashlib.sha256(open(os.path.join(d, "out-b200"), "rb").read()).digest()
             out["curves"][curve] = {"b200_input_to_proof_s": ours[-1] / 1e3 if ours else None,

@@ -22,7 +22,7 @@ def units():
 
 
 def sources():
-    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h"))]
+    out = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh", ".h", ".cpp"))]
     out.append(os.path.join(os.path.dirname(HERE), "include", "b200_msm.h"))
     return out
 
@@ -66,6 +66,11 @@ def build(force=False, verbose=False, extra_flags=None, out=None):
             objs.append(obj)
     subprocess.run([nvcc] + ccbin + ARCH + ["-shared", "-o", LIB + ".tmp"] + objs, check=True, cwd=CSRC)
     os.replace(LIB + ".tmp", LIB)
+    if LIB.endswith("libb200msm.so") and os.path.dirname(LIB) == HERE:
+        # the command-line prover: plain C++ over the C ABI (no CUDA headers, no libff)
+        cxx = HOST_CXX if os.path.exists(HOST_CXX) else "g++"
+        subprocess.run([cxx, "-O2", "-std=c++17", "-o", os.path.join(HERE, "b200_prove"), os.path.join(CSRC, "prove_main.cpp"),
+                        "-L" + HERE, "-lb200msm", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

@@ -126,6 +126,15 @@ int compute_h_impl(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_
 
 }  // namespace
 
+// out_dev[i] = in_dev[i] * k over Fr of the context's curve (device pointers; k: 24 words on the device), on `st`
+int b200msm_internal_fr_scale(b200msm_ctx *ctx, size_t n, const uint32_t *in_dev, const uint32_t *k_dev, uint32_t *out_dev, cudaStream_t st) {
+    const unsigned g = (unsigned)((n + 127) / 128);
+    if (ctx->curve == B200MSM_MNT4753) k_scale<ModB><<<g, 128, 0, st>>>(out_dev, in_dev, k_dev, (uint32_t)n);
+    else k_scale<ModA><<<g, 128, 0, st>>>(out_dev, in_dev, k_dev, (uint32_t)n);
+    CU(cudaGetLastError());
+    return B200MSM_OK;
+}
+
 extern "C" {
 
 int b200msm_compute_h(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out_host,

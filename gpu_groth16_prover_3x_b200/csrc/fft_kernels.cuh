@@ -189,6 +189,18 @@ __global__ void __launch_bounds__(128) k_pointwise_mul(uint32_t *a, const uint32
     st_fq(a + (size_t)i * NLIMB, x);
 }
 
+// out[i] = in[i] * k      (Fr, Montgomery: used to fold the proof's r into the B1-query scalars)
+template <class M>
+__global__ void __launch_bounds__(128) k_scale(uint32_t *out, const uint32_t *in, const uint32_t *k, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    fq_t x, y;
+    ld_fq(x, in + (size_t)i * NLIMB);
+    ld_fq(y, k);
+    fq_mul<M>(x, x, y);
+    st_fq(out + (size_t)i * NLIMB, x);
+}
+
 // a[i] = (a[i] * b[i] - c[i]) * zinv        (cuda_prover_piecewise.cu:29-39)
 template <class M>
 __global__ void __launch_bounds__(128) k_h_pointwise(uint32_t *a, const uint32_t *b, const uint32_t *c, const uint32_t *zinv, uint32_t n) {

@@ -529,6 +529,26 @@ int run_synthetic(b200msm_ctx *ctx, size_t n, const uint64_t *k_p0, const uint64
     return B200MSM_OK;
 }
 
+// out (Jacobian) = k * P for one affine point P and one Montgomery-form scalar k of Fr (the r * Bt1 of the proof
+// assembly, cuda_prover_piecewise.cu:198; the reference does it on the host with libff)
+template <class G>
+int run_scalar_mul(b200msm_ctx *ctx, const uint64_t *affine, const uint64_t *k_mont, uint64_t *out_xyz) {
+    typedef TailCfg<G> TC;
+    constexpr size_t EB = G::F::DEG * NLIMB * 4;
+    DevBuf p, k, o;
+    CU(cudaMalloc(&p.p, 2 * EB));
+    CU(cudaMalloc(&k.p, NLIMB * 4));
+    CU(cudaMalloc(&o.p, 3 * EB));
+    CU(cudaMemcpy(p.p, affine, 2 * EB, cudaMemcpyDefault));
+    CU(cudaMemcpy(k.p, k_mont, NLIMB * 4, cudaMemcpyDefault));
+    CU(cudaFuncSetAttribute(k_scalar_mul<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    k_scalar_mul<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>((const uint32_t *)p.p, (const uint32_t *)k.p, (uint32_t *)o.p);
+    CU(cudaGetLastError());
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out_xyz, o.p, 3 * EB, cudaMemcpyDefault));
+    return B200MSM_OK;
+}
+
 // throughput of the slab multiplier (Team::mul, operands in shared memory) at 4 / 8 / 12 warps per SM:
 // `iters` x 2 dependent products per lane.  Returns 10^9 Fq-tower products per second in *gops.
 template <class G>
@@ -576,5 +596,5 @@ int run_teammul_bench(b200msm_ctx *ctx, int blocks_per_sm, int iters, double *go
 
 template <class G>
 constexpr GroupOps make_group_ops() {
-    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>, &run_teammul_bench<G>};
+    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>, &run_teammul_bench<G>, &run_scalar_mul<G>};
 }

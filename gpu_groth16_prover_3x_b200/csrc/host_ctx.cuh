@@ -158,4 +158,5 @@ struct GroupOps {
     int (*synthetic)(b200msm_ctx *, size_t, const uint64_t *, const uint64_t *, BaseSet &);
     int (*build_tables)(b200msm_ctx *, BaseSet &);
     int (*teammul_bench)(b200msm_ctx *, int, int, double *);
+    int (*scalar_mul)(b200msm_ctx *, const uint64_t *, const uint64_t *, uint64_t *);
 };

@@ -279,6 +279,13 @@ int b200msm_to_affine(b200msm_ctx *ctx, int group, size_t n, const uint64_t *xyz
     return ops_for(ctx->curve, group).to_affine(ctx, n, xyz, out_affine);
 }
 
+int b200msm_scalar_mul(b200msm_ctx *ctx, int group, const uint64_t *affine, const uint64_t *k_mont, uint64_t *out_xyz) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!affine || !k_mont || !out_xyz || (group != B200MSM_G1 && group != B200MSM_G2)) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    CU(cudaSetDevice(ctx->device));
+    return ops_for(ctx->curve, group).scalar_mul(ctx, affine, k_mont, out_xyz);
+}
+
 int b200msm_bases_synthetic(b200msm_ctx *ctx, int group, size_t n, const uint64_t *k_p0_mont, const uint64_t *k_q_mont, int *slot) {
     if (!ctx) return B200MSM_ERR_ARG;
     if (!slot || !k_p0_mont || !k_q_mont || n == 0 || n >= (size_t(1) << 31) || (group != B200MSM_G1 && group != B200MSM_G2))

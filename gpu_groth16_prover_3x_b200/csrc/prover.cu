@@ -1,0 +1,158 @@
+// The whole `compute` step of the reference's GPU prover behind the C ABI: proving key resident in HBM, one
+// call per proof.  b200msm_prove is run_prover of cuda_prover_piecewise.cu:96-230 with
+//   * the five multi-exponentiations A, B1, B2, L, H on the engine (A and H ran on the CPU in the reference),
+//   * compute_H on the device (b200msm_compute_h),
+//   * the proof assembly  C = Ht + Lt + r * Bt1  and the three affine normalisations on the device
+//     (the reference: libff on the host, lines 198-204),
+// writing the proof bytes of groth16_output_write (A || B || C, affine, infinity as zeros;
+// libsnark/serialization.hpp:43-67).  It only composes the other entry points of include/b200_msm.h.
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "host_ctx.cuh"
+
+struct b200msm_key {
+    size_t d = 0, m = 0;
+    int slot[5] = {-1, -1, -1, -1, -1};  // A, B1, B2, L, H
+    uint32_t *w_dev = nullptr, *rw_dev = nullptr, *r_dev = nullptr;   // witness, r * witness, r (device, reused per proof)
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ready = nullptr;
+};
+
+int b200msm_internal_fr_scale(b200msm_ctx *ctx, size_t n, const uint32_t *in_dev, const uint32_t *k_dev, uint32_t *out_dev, cudaStream_t st);
+
+namespace {
+inline int g2_deg(const b200msm_ctx *ctx) { return ctx->curve == B200MSM_MNT4753 ? 2 : 3; }
+}
+
+extern "C" {
+
+void b200msm_key_free(b200msm_ctx *ctx, b200msm_key *key) {
+    if (!ctx || !key) return;
+    for (int s : key->slot)
+        if (s >= 0) b200msm_bases_free(ctx, s);
+    cudaSetDevice(ctx->device);
+    if (key->w_dev) cudaFree(key->w_dev);
+    if (key->rw_dev) cudaFree(key->rw_dev);
+    if (key->r_dev) cudaFree(key->r_dev);
+    if (key->ready) cudaEventDestroy(key->ready);
+    if (key->stream) cudaStreamDestroy(key->stream);
+    delete key;
+}
+
+int b200msm_key_load(b200msm_ctx *ctx, const void *params_image, size_t bytes, b200msm_key **out) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!params_image || !out || bytes < 16) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    *out = nullptr;
+    // layout of <curve>-parameters (generate_parameters.cpp:59-108): u64 d, u64 m, A[m+1] G1, B1[m+1] G1,
+    // B2[m+1] G2, L[m-1] G1, H[d] G1, every point affine x || y in Montgomery limbs
+    const uint64_t *p = static_cast<const uint64_t *>(params_image);
+    const size_t d = p[0], m = p[1], g1 = 24, g2 = 24 * (size_t)g2_deg(ctx);
+    if (m < 1 || d > (size_t(1) << 30) || m > (size_t(1) << 30)) return fail(ctx, B200MSM_ERR_ARG, "implausible d = %zu, m = %zu", d, m);
+    const size_t want = 16 + 8 * (2 * (m + 1) * g1 + (m + 1) * g2 + (m - 1) * g1 + d * g1);
+    if (bytes != want) return fail(ctx, B200MSM_ERR_ARG, "parameter image of %zu bytes, expected %zu for d = %zu, m = %zu", bytes, want, d, m);
+    b200msm_key *key = new b200msm_key;
+    key->d = d;
+    key->m = m;
+    p += 2;
+    const int group[5] = {B200MSM_G1, B200MSM_G1, B200MSM_G2, B200MSM_G1, B200MSM_G1};
+    const size_t count[5] = {m + 1, m + 1, m + 1, m - 1, d}, words[5] = {g1, g1, g2, g1, g1};
+    for (int q = 0; q < 5; ++q) {
+        int rc = b200msm_bases_upload(ctx, group[q], p, count[q], &key->slot[q]);
+        if (rc) { b200msm_key_free(ctx, key); return rc; }
+        p += count[q] * words[q];
+    }
+    const bool ok = cudaMalloc(&key->w_dev, (m + 1) * 96) == cudaSuccess && cudaMalloc(&key->rw_dev, (m + 1) * 96) == cudaSuccess &&
+                    cudaMalloc(&key->r_dev, 96) == cudaSuccess &&
+                    cudaStreamCreateWithFlags(&key->stream, cudaStreamNonBlocking) == cudaSuccess &&
+                    cudaEventCreateWithFlags(&key->ready, cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) { b200msm_key_free(ctx, key); return fail(ctx, B200MSM_ERR_OOM, "cannot allocate the witness buffers"); }
+    *out = key;
+    return B200MSM_OK;
+}
+
+int b200msm_key_load_file(b200msm_ctx *ctx, const char *path, b200msm_key **out) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!path || !out) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    FILE *f = fopen(path, "rb");
+    if (!f) return fail(ctx, B200MSM_ERR_ARG, "cannot open %s", path);
+    fseek(f, 0, SEEK_END);
+    const long n = ftell(f);
+    fseek(f, 0, SEEK_SET);
+    std::vector<char> buf(n > 0 ? (size_t)n : 0);
+    const bool ok = n > 0 && fread(buf.data(), 1, (size_t)n, f) == (size_t)n;
+    fclose(f);
+    if (!ok) return fail(ctx, B200MSM_ERR_ARG, "cannot read %s", path);
+    return b200msm_key_load(ctx, buf.data(), buf.size(), out);
+}
+
+int b200msm_key_info(const b200msm_key *key, uint64_t info[2]) {
+    if (!key || !info) return B200MSM_ERR_ARG;
+    info[0] = key->d;
+    info[1] = key->m;
+    return B200MSM_OK;
+}
+
+void *b200msm_pinned_alloc(size_t bytes) {
+    void *p = nullptr;
+    return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr;
+}
+void b200msm_pinned_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
+size_t b200msm_proof_bytes(const b200msm_ctx *ctx) { return ctx ? (size_t)(2 * 192 + 192 * g2_deg(ctx)) : 0; }
+size_t b200msm_input_bytes(const b200msm_key *key) { return key ? ((key->m + 1) + 3 * (key->d + 1) + 1) * 96 : 0; }
+
+int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_image, size_t bytes, uint8_t *proof) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!key || !input_image || !proof) return fail(ctx, B200MSM_ERR_ARG, "null pointer");
+    const size_t d = key->d, m = key->m;
+    if (bytes != b200msm_input_bytes(key)) return fail(ctx, B200MSM_ERR_ARG, "input image of %zu bytes, expected %zu", bytes, b200msm_input_bytes(key));
+    // layout of <curve>-input (main.cpp:35-85): w[m+1], ca[d+1], cb[d+1], cc[d+1], r -- Fr, Montgomery limbs
+    const uint64_t *w = static_cast<const uint64_t *>(input_image);
+    const uint64_t *ca = w + (m + 1) * 12, *cb = ca + (d + 1) * 12, *cc = cb + (d + 1) * 12, *r = cc + (d + 1) * 12;
+    const int dg = g2_deg(ctx);
+    uint64_t A[36], rB1[36], B2[108], L[36], H[36];
+    int rc;
+    // The witness crosses PCIe once; the B1 query runs on r * w so that its result is the r * Bt1 term of C directly
+    // (sum (r w_i) B1_i = r * sum w_i B1_i: the same group element, no 753-step scalar multiplication afterwards).
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaMemcpyAsync(key->w_dev, w, (m + 1) * 96, cudaMemcpyHostToDevice, key->stream));
+    CU(cudaMemcpyAsync(key->r_dev, r, 96, cudaMemcpyHostToDevice, key->stream));
+    if ((rc = b200msm_internal_fr_scale(ctx, m + 1, key->w_dev, key->r_dev, key->rw_dev, key->stream))) return rc;
+    CU(cudaEventRecord(key->ready, key->stream));
+    for (int l = 0; l < 4; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, key->ready, 0));
+    const uint64_t *wd = reinterpret_cast<const uint64_t *>(key->w_dev), *rwd = reinterpret_cast<const uint64_t *>(key->rw_dev);
+    // the four witness MSMs in flight together (cuda_prover_piecewise.cu:162-167), the H polynomial beside them
+    if ((rc = b200msm_msm_async(ctx, 0, key->slot[0], 0, wd, m + 1, A))) return rc;
+    if ((rc = b200msm_msm_async(ctx, 1, key->slot[1], 0, rwd, m + 1, rB1))) return rc;
+    if ((rc = b200msm_msm_async(ctx, 2, key->slot[2], 0, wd, m + 1, B2))) return rc;
+    if ((rc = b200msm_msm_async(ctx, 3, key->slot[3], 0, wd + 2 * 12, m - 1, L))) return rc;   // w[2..m] (:167)
+    const uint64_t *h_dev = nullptr;
+    rc = b200msm_compute_h(ctx, d, ca, cb, cc, nullptr, &h_dev);
+    int rcw = b200msm_wait(ctx, 0);
+    if (rc || rcw) { for (int l = 1; l < 4; ++l) b200msm_wait(ctx, l); return rc ? rc : rcw; }
+    rc = b200msm_msm_async(ctx, 0, key->slot[4], 0, h_dev, d, H);
+    for (int l = 1; l < 4; ++l) { rcw = b200msm_wait(ctx, l); if (!rc) rc = rcw; }
+    rcw = b200msm_wait(ctx, 0);
+    if (!rc) rc = rcw;
+    if (rc) return rc;
+    // C = Ht + Lt + r * Bt1  (:198-200); A and B2 as they are
+    uint64_t sum_in[108], C[36];
+    memcpy(sum_in, H, 288);
+    memcpy(sum_in + 36, L, 288);
+    memcpy(sum_in + 72, rB1, 288);
+    if ((rc = b200msm_fold(ctx, B200MSM_G1, sum_in, 3, C))) return rc;
+    uint64_t a_aff[24], b_aff[72], c_aff[24];
+    if ((rc = b200msm_to_affine(ctx, B200MSM_G1, 1, A, a_aff))) return rc;
+    if ((rc = b200msm_to_affine(ctx, B200MSM_G2, 1, B2, b_aff))) return rc;
+    if ((rc = b200msm_to_affine(ctx, B200MSM_G1, 1, C, c_aff))) return rc;
+    memcpy(proof, a_aff, 192);
+    memcpy(proof + 192, b_aff, (size_t)192 * dg);
+    memcpy(proof + 192 + 192 * dg, c_aff, 192);
+    return B200MSM_OK;
+}
+
+}  // extern "C"

@@ -65,6 +65,21 @@ def load_library():
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
     lib.b200msm_set_table_budget.argtypes = [vp, sz]
     lib.b200msm_set_accumulator.argtypes = [vp, ci]
+    lib.b200msm_scalar_mul.argtypes = [vp, ci, vp, vp, vp]
+    lib.b200msm_key_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
+    lib.b200msm_key_load_file.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
+    lib.b200msm_key_info.argtypes = [vp, _u64p]
+    lib.b200msm_key_free.argtypes = [vp, vp]
+    lib.b200msm_key_free.restype = None
+    lib.b200msm_proof_bytes.argtypes = [vp]
+    lib.b200msm_proof_bytes.restype = sz
+    lib.b200msm_input_bytes.argtypes = [vp]
+    lib.b200msm_input_bytes.restype = sz
+    lib.b200msm_prove.argtypes = [vp, vp, vp, sz, vp]
+    lib.b200msm_pinned_alloc.argtypes = [sz]
+    lib.b200msm_pinned_alloc.restype = vp
+    lib.b200msm_pinned_free.argtypes = [vp]
+    lib.b200msm_pinned_free.restype = None
     lib.b200msm_compute_h.argtypes = [vp, sz, vp, vp, vp, vp, ctypes.POINTER(vp)]
     lib.b200msm_compute_h_timings.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     lib.b200msm_fft_release.argtypes = [vp]
@@ -254,6 +269,37 @@ class MsmContext:
                  accumulate_launches=int(info[3]), kernel_launches=int(info[4]), bucket_sets=int(info[5]),
                  tables=int(info[6]), accumulator=int(info[7]))
         return d
+
+    def scalar_mul(self, group, affine, k_mont):
+        out = self._out(group)
+        self._check(self.lib.b200msm_scalar_mul(self._h, group, _ptr(affine), _ptr(k_mont), _ptr(out)))
+        return out
+
+    # ---- whole proofs (run_prover of cuda_prover_piecewise.cu:96-230) ----
+    def load_key(self, params):
+        """params: path of a <curve>-parameters file, or its bytes (numpy uint8 / bytes).  -> opaque key handle."""
+        key = ctypes.c_void_p()
+        if isinstance(params, str):
+            self._check(self.lib.b200msm_key_load_file(self._h, params.encode(), ctypes.byref(key)))
+        else:
+            buf = np.frombuffer(params, dtype=np.uint8) if isinstance(params, (bytes, bytearray)) else np.ascontiguousarray(params).view(np.uint8)
+            self._check(self.lib.b200msm_key_load(self._h, _ptr(buf), buf.size, ctypes.byref(key)))
+        return key
+
+    def key_info(self, key):
+        info = (ctypes.c_uint64 * 2)()
+        self._check(self.lib.b200msm_key_info(key, info))
+        return {"d": int(info[0]), "m": int(info[1])}
+
+    def free_key(self, key):
+        self.lib.b200msm_key_free(self._h, key)
+
+    def prove(self, key, input_image):
+        """input_image: bytes of the <curve>-input file (bytes or numpy uint8).  -> proof bytes (A || B || C affine)."""
+        buf = np.frombuffer(input_image, dtype=np.uint8) if isinstance(input_image, (bytes, bytearray)) else np.ascontiguousarray(input_image).view(np.uint8)
+        proof = np.zeros(self.lib.b200msm_proof_bytes(self._h), np.uint8)
+        self._check(self.lib.b200msm_prove(self._h, key, _ptr(buf), buf.size, _ptr(proof)))
+        return proof.tobytes()
 
     def compute_h(self, ca, cb, cc, to_host=True):
         """coefficients_for_H of the Groth16 prover (compute_H, cuda_prover_piecewise.cu:14-49) from the d + 1

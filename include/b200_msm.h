@@ -111,6 +111,30 @@ int b200msm_compute_h_timings(b200msm_ctx *ctx, float ms[2]);
 /* Free the FFT tables and work vectors (also done by b200msm_destroy). */
 void b200msm_fft_release(b200msm_ctx *ctx);
 
+/* k * P for one affine point and one Montgomery-form scalar of Fr -> Jacobian (the r * Bt1 of the proof
+ * assembly, cuda_prover_piecewise.cu:198, done by libff on the host in the reference). */
+int b200msm_scalar_mul(b200msm_ctx *ctx, int group, const uint64_t *affine, const uint64_t *k_mont, uint64_t *out_xyz);
+
+/* ---- the whole `compute` step --------------------------------------------------
+ * A proving key resident in HBM and one call per proof: replaces run_prover (cuda_prover_piecewise.cu:96-230)
+ * including B::read_params / load_points_affine (no preprocessed file), the five MSMs, compute_H, the assembly
+ * C = Ht + Lt + r * Bt1 and groth16_output_write.  `params_image` / `input_image` are the bytes of the reference's
+ * <curve>-parameters and <curve>-input files (generate_parameters.cpp:59-108, main.cpp:35-85; host memory);
+ * `proof` receives b200msm_proof_bytes() bytes, identical to the file the reference's provers write
+ * (A || B || C affine: 768 bytes for MNT4753, 960 for MNT6753).  Single GPU; uses lanes 0-3 of the context. */
+typedef struct b200msm_key b200msm_key;
+int b200msm_key_load(b200msm_ctx *ctx, const void *params_image, size_t bytes, b200msm_key **key);
+int b200msm_key_load_file(b200msm_ctx *ctx, const char *path, b200msm_key **key);
+int b200msm_key_info(const b200msm_key *key, uint64_t info[2]); /* d, m */
+void b200msm_key_free(b200msm_ctx *ctx, b200msm_key *key);
+size_t b200msm_proof_bytes(const b200msm_ctx *ctx);
+size_t b200msm_input_bytes(const b200msm_key *key);
+int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_image, size_t bytes, uint8_t *proof);
+/* Page-locked host memory for witness / scalar buffers (H2D at full PCIe rate, truly asynchronous uploads);
+ * plain malloc'ed memory works everywhere too, only slower.  NULL on failure. */
+void *b200msm_pinned_alloc(size_t bytes);
+void b200msm_pinned_free(void *p);
+
 /* Enqueue lane `lane` on a caller-owned CUDA stream (a cudaStream_t passed as void*; NULL restores the
  * internal stream).  The reference hands a cudaStream_t& back to its caller for the same purpose
  * (reduce.cu:131-135): ordering the MSM against the caller's own work and timing it with events. */

@@ -46,3 +46,35 @@ def test_proof_sha256_equals_reference_cpu_prover(fast_params, curve):
         b = os.path.join(d, name)
         assert os.path.getsize(ref_out) == os.path.getsize(b) == (768 if curve == "MNT4753" else 960)
         assert sha256(ref_out) == sha256(b), extra
+
+
+@pytest.mark.parametrize("curve", ["MNT4753", "MNT6753"])
+def test_whole_proof_through_the_c_abi(fast_params, curve):
+    """b200msm_key_load_file + b200msm_prove (key resident in HBM, one call per proof, proof assembly and affine
+    normalisation on the device, no libff anywhere) and the b200_prove command-line twin of the reference's
+    `cuda_prover_piecewise <curve> compute`: same bytes as the reference CPU prover."""
+    import gpu_groth16_prover_3x_b200 as pkg
+    d = fast_params
+    params, inp = os.path.join(d, "%s-parameters" % curve), os.path.join(d, "%s-input" % curve)
+    ref_out = os.path.join(d, curve + "-output-ref")
+    if not os.path.exists(ref_out):
+        subprocess.run([BINS[1], curve, "compute", params, inp, ref_out], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=1800)
+    want = open(ref_out, "rb").read()
+    with pkg.MsmContext(pkg.MNT4753 if curve == "MNT4753" else pkg.MNT6753, 0) as ctx:
+        key = ctx.load_key(params)
+        info = ctx.key_info(key)
+        assert info["m"] == info["d"] + 1
+        image = open(inp, "rb").read()
+        assert ctx.prove(key, image) == want
+        assert ctx.prove(key, image) == want           # a resident key proves again
+        with pytest.raises(pkg.MsmError):
+            ctx.prove(key, image[:-96])                # truncated witness
+        ctx.free_key(key)
+        with pytest.raises(pkg.MsmError):
+            ctx.load_key(open(params, "rb").read()[:-8])
+    cli = os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "b200_prove")
+    out = subprocess.run([cli, curve, "compute", params, inp, os.path.join(d, curve + "-output-cli"), "2"], check=True,
+                         capture_output=True, text=True, timeout=900).stdout
+    print(out)
+    assert sha256(os.path.join(d, curve + "-output-cli")) == hashlib.sha256(want).hexdigest()
+

@@ -18,9 +18,12 @@ for curve in MNT4753 MNT6753; do
   echo "=== $curve"
   t0=$(now); $REF/main $curve compute $curve-parameters $curve-input $curve-output-ref > main_$curve.log 2>&1
   echo "reference CPU prover (main $curve compute, $(nproc) threads): $(el $t0) s wall"
+  echo "-- product CLI (b200msm_key_load_file + b200msm_prove, no libff):"
+  $REPO/gpu_groth16_prover_3x_b200/b200_prove $curve compute $curve-parameters $curve-input $curve-output-cli 3
+  echo "-- reference driver with MSMs + H on the engine (tests/integration/b200_prover.cpp):"
   $REF/b200_prover $curve compute $curve-parameters $curve-input $curve-output-b200 1 gpu-h 3
   $REF/b200_prover $curve compute $curve-parameters $curve-input $curve-output-b200-cpuh 1 cpu-h 2 | grep -E "compute_H|Total time"
-  sha256sum $curve-output-ref $curve-output-b200 $curve-output-b200-cpuh
+  sha256sum $curve-output-ref $curve-output-cli $curve-output-b200 $curve-output-b200-cpuh
   if [ -x $REF/cuda_prover_piecewise ] && { [ $curve = MNT6753 ] || [ "${1:-}" = fast ]; }; then
     t0=$(now); $REF/main $curve preprocess $curve-parameters > pre_$curve.log 2>&1; echo "reference preprocess (31x table): $(el $t0) s, $(du -h ${curve}_preprocessed | cut -f1)"
     t0=$(now); $REF/cuda_prover_piecewise $curve compute $curve-parameters $curve-input $curve-output-refgpu > refgpu_$curve.log 2>&1
