@@ -78,3 +78,19 @@ def test_whole_proof_through_the_c_abi(fast_params, curve):
     print(out)
     assert sha256(os.path.join(d, curve + "-output-cli")) == hashlib.sha256(want).hexdigest()
 
+
+def test_sharded_prover_two_gpus(fast_params):
+    """Every query sharded by point range over two GPUs, partial points folded: same proof."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    d = fast_params
+    curve = "MNT4753"
+    params, inp = "%s-parameters" % curve, "%s-input" % curve
+    ref_out = os.path.join(d, curve + "-output-ref")
+    if not os.path.exists(ref_out):
+        subprocess.run([BINS[1], curve, "compute", params, inp, curve + "-output-ref"], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=1800)
+    subprocess.run([BINS[2], curve, "compute", params, inp, curve + "-output-2gpu", "2", "gpu-h", "1"], cwd=d, check=True,
+                   stdout=subprocess.DEVNULL, timeout=900)
+    assert sha256(ref_out) == sha256(os.path.join(d, curve + "-output-2gpu"))
+
