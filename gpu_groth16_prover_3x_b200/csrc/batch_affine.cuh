@@ -224,8 +224,19 @@ __global__ void __launch_bounds__(256) k_ba_plan(BaArgs a) {
         const bool valid = j < E;
         uint32_t s0 = 0, s1 = BA_NONE;
         bool s0_inf = false;
+        // the 32 outputs of a warp are consecutive: two full binary searches (its first and last output) bound
+        // the few-step search of every lane in between
+        const uint32_t jw0 = j - (uint32_t)lane;
+        uint32_t bb = 0;
+        if ((lane == 0 || lane == 31) && jw0 < E) bb = bucket_of(a.off_next, a.K, lane == 0 ? jw0 : min(jw0 + 31u, E - 1u));
+        const uint32_t b_first = __shfl_sync(0xffffffffu, bb, 0), b_last = __shfl_sync(0xffffffffu, bb, 31);
         if (valid) {
-            const uint32_t b = bucket_of(a.off_next, a.K, j);
+            uint32_t blo = b_first, bhi = b_last + 1u;   // invariant: off_next[blo] <= j < off_next[bhi]
+            while (bhi - blo > 1u) {
+                const uint32_t mid = blo + ((bhi - blo) >> 1);
+                if (a.off_next[mid] <= j) blo = mid; else bhi = mid;
+            }
+            const uint32_t b = blo;
             const uint32_t l = j - a.off_next[b];
             const uint32_t lo = a.off_cur[b], cnt = a.off_cur[b + 1] - lo;
             const uint32_t i0 = lo + 2u * l;
