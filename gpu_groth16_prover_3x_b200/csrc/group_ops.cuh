@@ -471,7 +471,7 @@ int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
     const size_t n = bs.n;
     CU(cudaMalloc(&jac.p, n * 3 * EB));
     CU(cudaMalloc(&pre.p, n * EB));
-    CU(cudaFuncSetAttribute(k_dbl_many<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
+    CU(cudaFuncSetAttribute(k_dbl_many<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DblCfg<G>::TS::SMEM));
     CU(cudaFuncSetAttribute(k_batch_normalise<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
@@ -481,8 +481,9 @@ int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
     const size_t runs = (n + B - 1) / B;
     const size_t tabw = n * 2 * (EB / 4);
     for (int t = 1; t < bs.NT; ++t) {
-        k_dbl_many<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, bs.c_tab * bs.G, bs.pts + (t - 1) * tabw,
-                                                                                            (uint32_t *)jac.p);
+        const unsigned dl = DblCfg<G>::TPB * 32;
+        k_dbl_many<G><<<(unsigned)((n + dl - 1) / dl), DblCfg<G>::TS::THREADS, DblCfg<G>::TS::SMEM>>>((uint32_t)n, bs.c_tab * bs.G, bs.pts + (t - 1) * tabw,
+                                                                                                    (uint32_t *)jac.p);
         k_batch_normalise<G><<<(unsigned)((runs + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>(
             (uint32_t)n, B, (const uint32_t *)jac.p, (uint32_t *)pre.p, bs.pts + t * tabw);
     }

@@ -111,27 +111,34 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_synth_bases(uint32_
 
 // ---- precomputed window tables -------------------------------------------------------------------
 // jac[i] = 2^s * in[i] for n affine points (infinity, encoded y == 0, stays infinity: Z = 2*Y*Z = 0).
+// A doubling needs six slots only, so this kernel runs with the 12-warps-per-SM team layout of k_batch_add.
 template <class G>
-__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_dbl_many(uint32_t n, int s_dbl, const uint32_t *in, uint32_t *jac) {
+struct DblCfg {
+    static constexpr int DEG = G::F::DEG;
+    static constexpr int TPB = DEG == 1 ? 4 : (DEG == 2 ? 2 : 1);
+    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 3 : 4);
+    typedef TeamSetup<G, 6, TPB> TS;
+};
+template <class G>
+__global__ void __launch_bounds__(DblCfg<G>::TS::THREADS, DblCfg<G>::MINB) k_dbl_many(uint32_t n, int s_dbl, const uint32_t *in, uint32_t *jac) {
     typedef typename G::F F;
-    typedef TailCfg<G> C;
-    typedef UtilSlots U;
+    typedef DblCfg<G> C;
     constexpr int EW = F::DEG * NLIMB;
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_flags[C::TPB][4];
     int team;
     const Team<F> T = C::TS::make(smem, s_flags, team);
-    const PtSlots s = {U::X1, U::Y1, U::Z1, U::X2, U::Y2, U::Z2, U::T0, U::T1, U::T2};
+    const PtSlots s = {0, 1, 2, 0, 0, 0, 3, 4, 5};   // no second operand
     const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + (threadIdx.x & 31);
     const bool act = id < n;
-    g2s(T, U::X1, in + (size_t)id * 2 * EW, act);
-    g2s(T, U::Y1, in + (size_t)id * 2 * EW + EW, act);
-    T.set_zero(U::X1, !act); T.set_zero(U::Y1, !act);
-    T.set_one(U::Z1);
+    g2s(T, s.X1, in + (size_t)id * 2 * EW, act);
+    g2s(T, s.Y1, in + (size_t)id * 2 * EW + EW, act);
+    T.set_zero(s.X1, !act); T.set_zero(s.Y1, !act);
+    T.set_one(s.Z1);
     T.sync();
     for (int i = 0; i < s_dbl; ++i) Ec<F>::dbl(T, s, true);
     T.sync();
-    store_jac(T, jac + (size_t)id * 3 * EW, U::X1, U::Y1, U::Z1, act);
+    store_jac(T, jac + (size_t)id * 3 * EW, s.X1, s.Y1, s.Z1, act);
 }
 
 // out[i] = affine(jac[i]), i < n: one lane per run of B consecutive points, one inversion per lane.
