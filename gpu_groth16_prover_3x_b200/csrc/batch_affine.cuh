@@ -62,17 +62,22 @@ MSM_DEVICE uint32_t pair_forward(const Team<F> &T, const BaSlots &s, bool valid,
 
 // Phase 2: slots X1, Y1, X2, Y2 hold the (signed) operands, PRE the prefix product, INV the running
 // inverse.  Leaves the sum in (X2, Y2) and advances INV.  Returns true when the result is infinity.
+// Split in two so that a kernel can let the ordinates arrive (cp.async) while the head runs: the head
+// touches X1, X2, PRE, INV -- and Y1 only on lanes that double.
 template <class F>
-MSM_DEVICE bool pair_backward(const Team<F> &T, const BaSlots &s, uint32_t code) {
+MSM_DEVICE void pair_backward_head(const Team<F> &T, const BaSlots &s, uint32_t code) {
     const bool dbl = code == BA_DBL;
-    const bool any_dbl = team_any(dbl);
     T.sub(s.X2, s.X2, s.X1);             // d = x2 - x1
-    if (any_dbl) T.dbl(s.X2, s.Y1, dbl); //   or 2 y1
+    if (team_any(dbl)) T.dbl(s.X2, s.Y1, dbl); //   or 2 y1
     T.set_one(s.X2, code >= BA_CANCEL);
     T.mul(s.PRE, s.INV, s.PRE);          // 1 / d
     T.mul(s.INV, s.INV, s.X2);           // inverse of the shorter prefix
+}
+template <class F>
+MSM_DEVICE bool pair_backward_tail(const Team<F> &T, const BaSlots &s, uint32_t code) {
+    const bool dbl = code == BA_DBL;
     T.sub(s.Y2, s.Y2, s.Y1);             // numerator y2 - y1
-    if (any_dbl) {                       //   or 3 x1^2 + a; d is dead on those lanes, X2 <- 0 so that x1 + x2 = 2 x1 below
+    if (team_any(dbl)) {                 //   or 3 x1^2 + a; d is dead on those lanes, X2 <- 0 so that x1 + x2 = 2 x1 below
         T.sqr(s.X2, s.X1, dbl);
         T.add(s.Y2, s.X2, s.X2, dbl);
         T.add(s.Y2, s.Y2, s.X2, dbl);
@@ -93,6 +98,11 @@ MSM_DEVICE bool pair_backward(const Team<F> &T, const BaSlots &s, uint32_t code)
     if (team_any(copy1)) { T.copy(s.X2, s.X1, copy1); T.copy(s.Y2, s.Y1, copy1); }
     if (team_any(cancel)) { T.set_zero(s.X2, cancel); T.set_zero(s.Y2, cancel); }
     return cancel;
+}
+template <class F>
+MSM_DEVICE bool pair_backward(const Team<F> &T, const BaSlots &s, uint32_t code) {
+    pair_backward_head(T, s, code);
+    return pair_backward_tail(T, s, code);
 }
 
 // After the forward pass INV holds each lane's product of denominators.  Replace it by the lane's own
@@ -283,9 +293,23 @@ __global__ void __launch_bounds__(256) k_ba_plan(BaArgs a) {
 template <class G>
 struct BaCfg {
     static constexpr int DEG = G::F::DEG;
-    static constexpr int NSLOT = 6;   // 18 KB of slab per warp: 12 warps per SM
+    // PREFETCH (experiment, off): three more slots double-buffer the gathers (cp.async straight into the slab
+    // while the previous addition is being computed); 27 KB of slab per warp then allow 8 warps per SM instead
+    // of 12.  Measured on B200 at 2^20: G1 56.3 ms against 54.3 ms without it (Fq2 150.9 vs 146.4) -- with the
+    // sources already pulled into L2 one step ahead (prefetch_coord) the gathers are not what the warps wait
+    // for, and the extra commit/wait traffic costs more than it hides.  8 warps per SM without PREFETCH
+    // (-DB200_BA_MINB=2) is within noise of 12 for G1 / Fq2 and 14 % slower for Fq3.
+#ifndef B200_BA_PREFETCH
+#define B200_BA_PREFETCH 0
+#endif
+    static constexpr bool PREFETCH = B200_BA_PREFETCH && DEG < 3;
+    static constexpr int NSLOT = PREFETCH ? 9 : 6;
     static constexpr int TPB = DEG == 1 ? 4 : (DEG == 2 ? 2 : 1);
-    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 3 : 4);
+#ifdef B200_BA_MINB
+    static constexpr int MINB = B200_BA_MINB;
+#else
+    static constexpr int MINB = PREFETCH ? 2 : (DEG == 1 ? 3 : (DEG == 2 ? 3 : 4));
+#endif
     typedef TeamSetup<G, NSLOT, TPB> TS;
 };
 
@@ -311,7 +335,8 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
     int team;
     const Team<F> T = C::TS::make(smem, s_flags, team);
     const int lane = threadIdx.x & 31;
-    const BaSlots s = {0, 1, 2, 3, 4, 5};
+    BaSlots s = {0, 1, 2, 3, 4, 5};
+    int NX1 = 6, NX2 = 7, NPRE = 8;   // spare slots of the double buffer (PREFETCH only)
     const uint32_t *in = FIRST ? a.bases : a.in_pts;
 
     if (blockIdx.x == 0 && threadIdx.x == 0) *a.nrounds = a.round + 1;
@@ -361,8 +386,24 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
                 prefetch_coord(T, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW);
             }
             nxt2 = (i + 2 < B && p + 64u < E) ? a.pairs[p + 64u] : idle;
-            g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
-            g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
+            if (C::PREFETCH) {
+                if (i == 0) {
+                    g2s_async(T, s.X1, in + (size_t)r1 * AFFW, valid);
+                    g2s_async(T, s.X2, in + (size_t)r2 * AFFW, valid);
+                    async_commit();
+                }
+                const bool more = i + 1 < B;
+                if (more) {      // next step's abscissae land in the spare slots while this step computes
+                    const bool nv = p + 32u < E;
+                    g2s_async(T, NX1, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, nv);
+                    g2s_async(T, NX2, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW, nv);
+                    async_commit();
+                    async_wait<1>();
+                } else async_wait<0>();
+            } else {
+                g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
+                g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
+            }
             const uint32_t code = pair_forward(T, s, valid, valid, [&](bool pred) {
                 g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, pred);
                 g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, pred);
@@ -371,6 +412,7 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
             if (valid && T.comp == 0) a.out_inf[j] = (uint8_t)code;   // parked until the backward pass
             s2g(T, a.out_pts + (size_t)j * AFFW, s.INV, valid);       // exclusive prefix, parked in the output slot
             T.mul(s.INV, s.INV, s.X2);
+            if (C::PREFETCH) { int t = s.X1; s.X1 = NX1; NX1 = t; t = s.X2; s.X2 = NX2; NX2 = t; }
         }
         // ---- one inversion for the whole tile
         tile_inverse(T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
@@ -395,16 +437,48 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
             }
             nxt2 = (i > 1 && p - 64u < E) ? a.pairs[p - 64u] : idle;
             const uint32_t code = valid ? a.out_inf[j] : (uint32_t)BA_IDLE;
-            g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
-            g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);
-            g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
-            g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
-            g2s(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
-            if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, valid); T.neg_if(s.Y2, s.Y2, d.y >> 31, valid); }
-            const bool res_inf = pair_backward(T, s, code);
+            bool res_inf;
+            if (C::PREFETCH) {
+                if (i == (int)B - 1) {   // first step of the pass: nothing was prefetched for it
+                    g2s_async(T, s.X1, in + (size_t)r1 * AFFW, valid);
+                    g2s_async(T, s.X2, in + (size_t)r2 * AFFW, valid);
+                    g2s_async(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
+                    async_commit();
+                }
+                g2s_async(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);      // needed after two products
+                g2s_async(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
+                async_commit();
+                const bool more = i > 0;
+                if (more) {              // next step: abscissae and prefix into the spare slots
+                    const bool nv = p - 32u < E;
+                    g2s_async(T, NX1, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, nv);
+                    g2s_async(T, NX2, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW, nv);
+                    g2s_async(T, NPRE, a.out_pts + (size_t)nxt.z * AFFW, nv);
+                    async_commit();
+                    async_wait<2>();
+                } else async_wait<1>();
+                if (team_any(code == BA_DBL)) { if (more) async_wait<1>(); else async_wait<0>(); }
+                if (FIRST && team_any(code == BA_DBL)) T.neg_if(s.Y1, s.Y1, d.x >> 31, valid);
+                pair_backward_head(T, s, code);
+                if (more) async_wait<1>(); else async_wait<0>();
+                if (FIRST) {
+                    if (!team_any(code == BA_DBL)) T.neg_if(s.Y1, s.Y1, d.x >> 31, valid);
+                    T.neg_if(s.Y2, s.Y2, d.y >> 31, valid);
+                }
+                res_inf = pair_backward_tail(T, s, code);
+            } else {
+                g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
+                g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);
+                g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
+                g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
+                g2s(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
+                if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, valid); T.neg_if(s.Y2, s.Y2, d.y >> 31, valid); }
+                res_inf = pair_backward(T, s, code);
+            }
             s2g(T, a.out_pts + (size_t)j * AFFW, s.X2, valid);
             s2g(T, a.out_pts + (size_t)j * AFFW + EW, s.Y2, valid);
             if (valid && T.comp == 0) a.out_inf[j] = res_inf ? 1 : 0;
+            if (C::PREFETCH) { int t = s.X1; s.X1 = NX1; NX1 = t; t = s.X2; s.X2 = NX2; NX2 = t; t = s.PRE; s.PRE = NPRE; NPRE = t; }
         }
     }
 }

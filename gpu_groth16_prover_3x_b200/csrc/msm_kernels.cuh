@@ -118,6 +118,9 @@ __device__ __forceinline__ void g2s_async(const Team<F> &T, int slot, const uint
     }
 }
 __device__ __forceinline__ void async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <class F>
 __device__ __forceinline__ void load_jac(const Team<F> &T, int X, int Y, int Z, const uint32_t *g, bool pred) {
