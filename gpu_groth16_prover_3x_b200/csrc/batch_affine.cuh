@@ -350,6 +350,7 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
     const uint4 idle = make_uint4(0u, 0u, 0u, 0u);
     __shared__ uint32_t s_B[C::TPB];
 
+    bool first_tile = true;
     for (;;) {
         T.sync();
         if (T.comp == 0 && lane == 0) {
@@ -360,6 +361,11 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
                 const uint32_t rem = E > cur ? E - cur : 0u;
                 Bt = (rem + teams * 32u - 1u) / (teams * 32u);
                 Bt = Bt < 16u ? 16u : (Bt > (uint32_t)BA_BMAX ? (uint32_t)BA_BMAX : Bt);
+#ifdef B200_BA_STAGGER
+                // (experiment, off: measured 48.3 vs 47.3 ms) all teams start a round together; first tiles of
+                // different lengths keep their forward / inversion / backward phases from lining up across the SM
+                if (first_tile) Bt = max(16u, Bt * (((blockIdx.x + (uint32_t)team) & 3u) + 1u) / 4u);
+#endif
             }
             s_tile[team] = atomicAdd(a.tile_counter + a.round, 32u * Bt);
             s_B[team] = Bt;
@@ -367,6 +373,7 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
         T.sync();
         const uint32_t base = s_tile[team];
         const uint32_t B = s_B[team];
+        first_tile = false;
         if (base >= E) break;
 
         // ---- forward: denominators and prefix products
