@@ -139,6 +139,9 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) cfg = {bs.c_tab, digits_for(bs.c_tab), bs.NT, bs.G};
     else cfg = choose_cfg(n, DEG, ctx->c_override, 0, false);
     const int c = cfg.c;
+    // 32-bit positions in the sorted list and 31-bit table rows (entry = row | sign << 31)
+    if ((uint64_t)n * (uint64_t)cfg.Wd >= (uint64_t(1) << 32) - 4096 || (uint64_t)bs.n * (uint64_t)cfg.NT >= (uint64_t(1) << 31))
+        return fail(ctx, B200MSM_ERR_ARG, "n = %zu with %d digits per scalar exceeds the 2^32 sorted entries of one call; shard the MSM", n, cfg.Wd);
     Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
     int rc = grow_arena(ctx, ln, probe.bytes);
     if (rc) return rc;
