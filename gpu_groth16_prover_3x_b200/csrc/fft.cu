@@ -135,6 +135,16 @@ int b200msm_internal_fr_scale(b200msm_ctx *ctx, size_t n, const uint32_t *in_dev
     return B200MSM_OK;
 }
 
+// internal (prover.cu): build the domain tables for d + 1 points ahead of the first proof
+int b200msm_internal_fft_prepare(b200msm_ctx *ctx, size_t d) {
+    int logm = 0;
+    while ((size_t(1) << logm) < d + 1) ++logm;
+    if ((size_t(1) << logm) != d + 1) return fail(ctx, B200MSM_ERR_ARG, "d + 1 = %zu is not a power of two", d + 1);
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->curve == B200MSM_MNT4753) return logm <= ModB::TWO_ADICITY ? fft_prepare<ModB>(ctx, logm) : fail(ctx, B200MSM_ERR_ARG, "domain too large");
+    return logm <= ModA::TWO_ADICITY ? fft_prepare<ModA>(ctx, logm) : fail(ctx, B200MSM_ERR_ARG, "domain too large");
+}
+
 extern "C" {
 
 int b200msm_compute_h(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out_host,

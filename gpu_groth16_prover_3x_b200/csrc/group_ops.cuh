@@ -106,6 +106,19 @@ int grow_arena(b200msm_ctx *ctx, Lane &ln, size_t bytes) {
     return B200MSM_OK;
 }
 
+// Size lane `li`'s arena for MSMs of n points over `bs` and set the kernels' shared-memory attributes now, so
+// that the first MSM does not pay for them (b200msm_key_load warms every lane it is going to use).
+template <class G>
+int reserve_lane(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t n) {
+    constexpr int DEG = G::F::DEG;
+    if (n == 0) return B200MSM_OK;
+    TabCfg cfg;
+    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) cfg = {bs.c_tab, digits_for(bs.c_tab), bs.NT, bs.G};
+    else cfg = choose_cfg(n, DEG, ctx->c_override, 0, false);
+    Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
+    return grow_arena(ctx, ctx->lanes[li], probe.bytes);
+}
+
 // Enqueue one MSM on lane `li`.  scalars: host or device pointer (Montgomery Fr).
 template <class G>
 int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, const uint64_t *scalars, size_t n,
@@ -600,5 +613,5 @@ int run_teammul_bench(b200msm_ctx *ctx, int blocks_per_sm, int iters, double *go
 
 template <class G>
 constexpr GroupOps make_group_ops() {
-    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>, &run_teammul_bench<G>, &run_scalar_mul<G>};
+    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>, &run_teammul_bench<G>, &run_scalar_mul<G>, &reserve_lane<G>};
 }

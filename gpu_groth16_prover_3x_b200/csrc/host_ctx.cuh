@@ -159,4 +159,5 @@ struct GroupOps {
     int (*build_tables)(b200msm_ctx *, BaseSet &);
     int (*teammul_bench)(b200msm_ctx *, int, int, double *);
     int (*scalar_mul)(b200msm_ctx *, const uint64_t *, const uint64_t *, uint64_t *);
+    int (*reserve)(b200msm_ctx *, int, const BaseSet &, size_t);
 };

@@ -279,6 +279,14 @@ int b200msm_to_affine(b200msm_ctx *ctx, int group, size_t n, const uint64_t *xyz
     return ops_for(ctx->curve, group).to_affine(ctx, n, xyz, out_affine);
 }
 
+// internal (prover.cu): pre-size lane `lane` for MSMs of n points over base set `slot`
+int b200msm_internal_reserve(b200msm_ctx *ctx, int lane, int slot, size_t n) {
+    if (!ctx || lane < 0 || lane >= NLANES || slot < 0 || slot >= (int)ctx->sets.size() || !ctx->sets[slot].used) return B200MSM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    const BaseSet &bs = ctx->sets[slot];
+    return ops_for(ctx->curve, bs.group).reserve(ctx, lane, bs, n);
+}
+
 int b200msm_scalar_mul(b200msm_ctx *ctx, int group, const uint64_t *affine, const uint64_t *k_mont, uint64_t *out_xyz) {
     if (!ctx) return B200MSM_ERR_ARG;
     if (!affine || !k_mont || !out_xyz || (group != B200MSM_G1 && group != B200MSM_G2)) return fail(ctx, B200MSM_ERR_ARG, "bad argument");

@@ -21,6 +21,8 @@ struct b200msm_key {
 };
 
 int b200msm_internal_fr_scale(b200msm_ctx *ctx, size_t n, const uint32_t *in_dev, const uint32_t *k_dev, uint32_t *out_dev, cudaStream_t st);
+extern "C" int b200msm_internal_reserve(b200msm_ctx *ctx, int lane, int slot, size_t n);
+int b200msm_internal_fft_prepare(b200msm_ctx *ctx, size_t d);
 
 namespace {
 inline int g2_deg(const b200msm_ctx *ctx) { return ctx->curve == B200MSM_MNT4753 ? 2 : 3; }
@@ -68,6 +70,14 @@ int b200msm_key_load(b200msm_ctx *ctx, const void *params_image, size_t bytes, b
                     cudaStreamCreateWithFlags(&key->stream, cudaStreamNonBlocking) == cudaSuccess &&
                     cudaEventCreateWithFlags(&key->ready, cudaEventDisableTiming) == cudaSuccess;
     if (!ok) { b200msm_key_free(ctx, key); return fail(ctx, B200MSM_ERR_OOM, "cannot allocate the witness buffers"); }
+    // warm everything the first proof would otherwise pay for: lane arenas (A and H share lane 0), domain tables
+    int rc = b200msm_internal_reserve(ctx, 0, key->slot[0], m + 1);
+    if (!rc) rc = b200msm_internal_reserve(ctx, 0, key->slot[4], d);
+    if (!rc) rc = b200msm_internal_reserve(ctx, 1, key->slot[1], m + 1);
+    if (!rc) rc = b200msm_internal_reserve(ctx, 2, key->slot[2], m + 1);
+    if (!rc) rc = b200msm_internal_reserve(ctx, 3, key->slot[3], m - 1);
+    if (!rc) rc = b200msm_internal_fft_prepare(ctx, d);
+    if (rc) { b200msm_key_free(ctx, key); return rc; }
     *out = key;
     return B200MSM_OK;
 }
