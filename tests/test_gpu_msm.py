@@ -232,3 +232,34 @@ def test_full_size_properties(ctxs, oracle, curve, group, log_n):
     dev = torch.from_numpy(vals.view(np.int64)).cuda()
     assert (affine(oracle, curve, group, ctx.msm(slot, dev, n)) == want).all()
     ctx.free_bases(slot)
+
+
+@pytest.mark.parametrize("curve,group,log_n", [(0, 1, 18), (1, 2, 14)])
+def test_skewed_witness_distribution(ctxs, oracle, curve, group, log_n):
+    """Real witnesses are not uniform: half of the scalars 0, a quarter 1, an eighth 2, a few r-1 and small
+    values, the rest random.  All the ones land in ONE bucket (a 2^(log_n-2)-point bucket needs log_n-2 rounds of
+    pairwise additions); the result is checked with the closed form of the structured base set."""
+    n = 1 << log_n
+    r = po.fr_modulus(curve)
+    rng = np.random.default_rng(11)
+    sc = po.gen_scalars(curve, 1 << 10, 99).reshape(-1, 12)
+    sc = np.tile(sc, (n >> 10, 1))                      # cheap "random" part
+    kind = rng.integers(0, 16, size=n)
+    one, two = po.int_to_limbs(po.R % r), po.int_to_limbs(2 * po.R % r)
+    rm1, small = po.int_to_limbs((r - 1) * po.R % r), po.int_to_limbs(12345 * po.R % r)
+    sc[kind < 8] = 0
+    sc[(kind >= 8) & (kind < 12)] = one
+    sc[(kind >= 12) & (kind < 14)] = two
+    sc[kind == 14] = np.where((np.arange(n)[kind == 14] % 2 == 0)[:, None], rm1[None, :], small[None, :])
+    sc = np.ascontiguousarray(sc).reshape(-1)
+    ctx = ctxs[curve]
+    k0, k1 = (po.int_to_limbs(po.sha512_rng_ints(r, s, 1)[0] * po.R % r) for s in (1000001, 1000002))
+    slot = ctx.synthetic_bases(group, n, k0, k1)
+    try:
+        got = affine(oracle, curve, group, ctx.msm(slot, sc, n))
+        t = ctx.last_timings()
+        print("skewed witness 2^%d: %.2f ms" % (log_n, t["total"]))
+        assert (got == oracle.msm_closed_form(curve, group, sc)).all()
+    finally:
+        ctx.free_bases(slot)
+
