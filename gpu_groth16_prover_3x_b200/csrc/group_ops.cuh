@@ -299,6 +299,11 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     ++launches;
     CU(cudaEventRecord(ln.ev[4], st));
     CU(cudaMemcpyAsync(ln.h_result, a.result, JACW * 4, cudaMemcpyDeviceToHost, st));
+    ln.ctl_rounds = 0;
+    if (batched && p.ba_rounds <= 32) {
+        CU(cudaMemcpyAsync(ln.h_ctl, p.ba_ctl, (size_t)(3 * p.ba_rounds + 4) * 4, cudaMemcpyDeviceToHost, st));
+        ln.ctl_rounds = p.ba_rounds;
+    }
     CU(cudaEventRecord(ln.ev[5], st));
     CU(cudaGetLastError());
 

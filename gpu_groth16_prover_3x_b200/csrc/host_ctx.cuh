@@ -48,6 +48,8 @@ struct Lane {
     char *arena = nullptr;
     size_t arena_bytes = 0;
     uint32_t *h_result = nullptr;  // pinned staging for the Jacobian result
+    uint32_t *h_ctl = nullptr;     // pinned copy of the batched-affine control block (rounds, occupancies, pair counts)
+    int ctl_rounds = 0;            // rounds enqueued by the last MSM (0: not a batched-affine MSM)
     uint64_t *user_out = nullptr;
     size_t out_words = 0;
     bool pending = false;
@@ -102,13 +104,16 @@ int fail(b200msm_ctx *ctx, int code, const char *fmt, ...) {
 inline int degree_of(int curve, int group) { return group == B200MSM_G1 ? 1 : (curve == B200MSM_MNT4753 ? 2 : 3); }
 
 // ---- window-size / table choice ---------------------------------------------------------------
-// Time model in nanoseconds, calibrated on B200 (profiles/): one mixed addition per point and digit in
-// k_accumulate, one bucket in the running-sum reduction, and the serial window combine (c doublings per
-// bucket set after the first; a lone lane runs them at the latency of one Fq product each).
+// Time model in nanoseconds, calibrated on B200 (profiles/, tools/c_sweep.py): ~1.2 ns per batched-affine
+// addition (one per point and digit), ~10 ns per bucket in the running-sum reduction, ~0.3 ms of latency per
+// round of pairwise additions, and the serial window combine (c doublings per bucket set after the first).
+// The number of rounds is log2 of the LARGEST bucket: besides the average occupancy that is the top window,
+// which holds only rem = 754 - (Wd - 1) c bits and therefore piles n / 2^(rem-1) points on each of its few
+// buckets (c = 16: rem = 2, a quarter of all points in one bucket) -- widths with a short top window lose.
 struct TabCfg { int c, Wd, NT, G; };
 inline int digits_for(int c) { return (MNT753_NUM_BITS + 1 + c - 1) / c; }
 
-TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bool tables) {
+inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bool tables) {
     const double k = deg == 1 ? 1.0 : (deg == 2 ? 3.0 : 6.0);
     const size_t affb = (size_t)2 * deg * NLIMB * 4;
     TabCfg best = {2, digits_for(2), 1, digits_for(2)};
@@ -126,8 +131,13 @@ TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bool tabl
         const int G = (Wd + (int)nt - 1) / (int)nt;
         const int NT = (Wd + G - 1) / G;
         const double NB = double(1u << (c - 1));
-        const double cost = double(Wd) * double(n) * 1.63 * k + double(G) * NB * 8.6 * k + double(G - 1) * c * 40000.0 * deg +
-                            double(G) * 60000.0 * deg;
+        const int rem = MNT753_NUM_BITS + 1 - (Wd - 1) * c;                       // bits of the top window
+        const double avg = double(n) * NT / NB;                                     // digits per bucket of a set
+        const double top = rem >= c ? 0.0 : double(n) / double(1u << (rem > 1 ? rem - 1 : 0));
+        double rounds = 1.0;
+        for (double occ = avg + top; occ > 1.0; occ *= 0.5) rounds += 1.0;
+        const double cost = double(Wd) * double(n) * 1.2 * k + double(G) * NB * 10.0 * k + double(G - 1) * c * 40000.0 * deg +
+                            rounds * 300000.0 * (deg == 1 ? 1.0 : deg * 0.8) + double(G) * 60000.0 * deg;
         if (cost < best_cost) { best_cost = cost; best = {c, Wd, NT, G}; }
     }
     return best;

@@ -185,6 +185,7 @@ int b200msm_create(int curve, int device, b200msm_ctx **out) {
         ok = ok && cudaStreamCreateWithFlags(&ln.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int e = 0; e <= NCOPY && ok; ++e) ok = cudaEventCreateWithFlags(&ln.ev_copy[e], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_result, 3 * 3 * NLIMB * 4) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ln.h_ctl, (3 * 32 + 8) * 4) == cudaSuccess;
         if (!ok) { b200msm_destroy(ctx); return B200MSM_ERR_CUDA; }
     }
     *out = ctx;
@@ -200,6 +201,7 @@ void b200msm_destroy(b200msm_ctx *ctx) {
         if (ln.stream) cudaStreamSynchronize(ln.stream);
         if (ln.arena) cudaFree(ln.arena);
         if (ln.h_result) cudaFreeHost(ln.h_result);
+        if (ln.h_ctl) cudaFreeHost(ln.h_ctl);
         for (int e = 0; e < NEVENTS; ++e) if (ln.ev[e]) cudaEventDestroy(ln.ev[e]);
         for (int e = 0; e <= NCOPY; ++e) if (ln.ev_copy[e]) cudaEventDestroy(ln.ev_copy[e]);
         if (ln.copy_stream) cudaStreamDestroy(ln.copy_stream);
@@ -363,6 +365,27 @@ int b200msm_set_window_bits(b200msm_ctx *ctx, int c) {
     if (!ctx) return B200MSM_ERR_ARG;
     if (c != 0 && (c < 2 || c > 22)) return fail(ctx, B200MSM_ERR_ARG, "window bits %d outside [2, 22]", c);
     ctx->c_override = c;
+    return B200MSM_OK;
+}
+
+int b200msm_last_rounds(b200msm_ctx *ctx, int lane, uint64_t info[4], uint32_t *pairs_per_round, size_t max_rounds) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (lane < 0 || lane >= NLANES || !info) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    const Lane &ln = ctx->lanes[lane];
+    if (ln.pending) return fail(ctx, B200MSM_ERR_ARG, "lane %d still has an un-waited MSM", lane);
+    const int R = ln.ctl_rounds;
+    memset(info, 0, 4 * sizeof(uint64_t));
+    if (R == 0) return B200MSM_OK;
+    const uint32_t *ctl = ln.h_ctl;   // nrounds | maxcnt[R + 1] | tile_counter[R] | npairs[R]
+    info[0] = ctl[0];
+    info[1] = (uint64_t)R;
+    info[2] = ctl[1];
+    uint64_t adds = 0;
+    for (int r = 0; r < R; ++r) {
+        adds += ctl[2 + 2 * R + r];
+        if (pairs_per_round && (size_t)r < max_rounds) pairs_per_round[r] = ctl[2 + 2 * R + r];
+    }
+    info[3] = adds;
     return B200MSM_OK;
 }
 

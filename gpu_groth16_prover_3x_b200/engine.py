@@ -86,6 +86,7 @@ def load_library():
     lib.b200msm_fft_release.restype = None
     lib.b200msm_bases_info.argtypes = [vp, ci, _u64p]
     lib.b200msm_last_timings.argtypes = [vp, ci, ctypes.POINTER(ctypes.c_float), _u64p]
+    lib.b200msm_last_rounds.argtypes = [vp, ci, _u64p, ctypes.POINTER(ctypes.c_uint32), sz]
     lib.b200msm_microbench.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double)]
     lib.b200msm_selftest_field.argtypes = [vp, ci, ci, sz, vp, vp, vp]
     lib.b200msm_selftest_point.argtypes = [vp, ci, ci, sz, vp, vp, vp, vp]
@@ -328,6 +329,13 @@ class MsmContext:
         self._check(self.lib.b200msm_bases_info(self._h, slot, info))
         return dict(points=int(info[0]), table_window_bits=int(info[1]), tables=int(info[2]), bucket_sets=int(info[3]),
                     bytes=int(info[4]), table_build_ms=int(info[5]) / 1e3)
+
+    def last_rounds(self, lane=0):
+        info = (ctypes.c_uint64 * 4)()
+        pairs = (ctypes.c_uint32 * 32)()
+        self._check(self.lib.b200msm_last_rounds(self._h, lane, info, pairs, 32))
+        return dict(rounds=int(info[0]), rounds_enqueued=int(info[1]), max_bucket_occupancy=int(info[2]),
+                    additions=int(info[3]), pairs_per_round=[int(x) for x in pairs[:int(info[0])]])
 
     def microbench(self, kind, iters=4096):
         g = ctypes.c_double()

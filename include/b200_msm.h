@@ -156,6 +156,11 @@ int b200msm_set_window_bits(b200msm_ctx *ctx, int c);
  * MSM, [5] = bucket sets G, [6] = window tables used NT, [7] = accumulator mode. */
 int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[8]);
 
+/* Batched-affine rounds of the most recent completed MSM on `lane`: info[0] = rounds executed, [1] = rounds
+ * enqueued (worst case), [2] = largest bucket occupancy after the sort, [3] = affine additions performed;
+ * pairs_per_round (may be NULL) receives the additions of each round.  All zero for the Jacobian accumulator. */
+int b200msm_last_rounds(b200msm_ctx *ctx, int lane, uint64_t info[4], uint32_t *pairs_per_round, size_t max_rounds);
+
 /* Synthetic microbenchmarks used by bench.py for the roofline denominator: runs `iters`
  * dependent-chain iterations of the named instruction mix on every SM and returns the achieved
  * rate in 10^9 operations per second (a 32x32->64 multiply-accumulate counts as one operation).

@@ -25,4 +25,5 @@ for i in range(reps):
     t0 = time.perf_counter()
     ctx.msm(slot, sc, n)
     print("msm %d: wall %.2f ms" % (i, (time.perf_counter() - t0) * 1e3), ctx.last_timings())
+print(ctx.last_rounds())
 ctx.close()
