@@ -304,11 +304,24 @@ struct BaCfg {
 #endif
     static constexpr bool PREFETCH = B200_BA_PREFETCH && DEG < 3;
     static constexpr int NSLOT = PREFETCH ? 9 : 6;
+    // ONEBLOCK (default): the twelve warps of an SM form ONE block of 384 threads instead of three blocks of four
+    // warps (four of three for Fq3).  Same occupancy, same code -- but the multiplier measures 7.5-7.7 G modmul/s
+    // with twelve warps in one block against 6.65 as 3 x 128, 4 x 96, 6 x 64 or 12 x 32 threads
+    // (tools/mul_sched_probe.cu, profiles/r01_mul_sched_probe.txt), and the accumulation follows: 2^20 G1
+    // 47.2 -> 43.9 ms, MNT6753 G2 2^18 83.2 -> 69.4 ms.
+#ifndef B200_BA_ONEBLOCK
+#define B200_BA_ONEBLOCK 1
+#endif
+#if B200_BA_ONEBLOCK
+    static constexpr int TPB = 12 / DEG;
+    static constexpr int MINB = 1;
+#else
     static constexpr int TPB = DEG == 1 ? 4 : (DEG == 2 ? 2 : 1);
 #ifdef B200_BA_MINB
     static constexpr int MINB = B200_BA_MINB;
 #else
     static constexpr int MINB = PREFETCH ? 2 : (DEG == 1 ? 3 : (DEG == 2 ? 3 : 4));
+#endif
 #endif
     typedef TeamSetup<G, NSLOT, TPB> TS;
 };

@@ -9,6 +9,7 @@
 
 #include "../../gpu_groth16_prover_3x_b200/csrc/curves.cuh"
 #include "../../gpu_groth16_prover_3x_b200/csrc/batch_affine.cuh"
+#include "../../gpu_groth16_prover_3x_b200/csrc/fq_fp64.cuh"
 
 using namespace mnt753;
 
@@ -160,14 +161,15 @@ int emu_point_op(int curve, int group, int op, const uint64_t *acc, const uint64
     return -1;
 }
 // scalar-field helper used by the digit kernel: Montgomery -> integer
-// both multiplier implementations on register operands: which = 0 CIOS (engine), 1 reduced-radix (experiment)
+// the multiplier implementations on register operands: which = 0 CIOS (engine), 1 reduced-radix (experiment),
+// 2 FP64-pipe form (fq_fp64.cuh, experiment)
 int emu_fq_mul(int modulus, int which, size_t n, const uint64_t *a, const uint64_t *b, uint64_t *out) {
     for (size_t i = 0; i < n; ++i) {
         fq_t x, y, r;
         memcpy(x, a + 12 * i, 96);
         memcpy(y, b + 12 * i, 96);
-        if (modulus == 0) { if (which) fq_mul_rr<ModA>(r, x, y); else fq_mul<ModA>(r, x, y); }
-        else { if (which) fq_mul_rr<ModB>(r, x, y); else fq_mul<ModB>(r, x, y); }
+        if (modulus == 0) { if (which == 2) fq_mul_fp<ModA>(r, x, y); else if (which) fq_mul_rr<ModA>(r, x, y); else fq_mul<ModA>(r, x, y); }
+        else { if (which == 2) fq_mul_fp<ModB>(r, x, y); else if (which) fq_mul_rr<ModB>(r, x, y); else fq_mul<ModB>(r, x, y); }
         memcpy(out + 12 * i, r, 96);
     }
     return 0;

@@ -130,8 +130,8 @@ def test_emu_point_chain_random_z(emu, oracle, curve, group):
 
 @pytest.mark.parametrize("modulus", [0, 1])
 def test_emu_both_multipliers(emu, oracle, golden, modulus):
-    """The 32-bit CIOS product (engine) and the reduced-radix experiment (kept as a microbenchmark) agree
-    with the oracle on edge values and random operands."""
+    """The 32-bit CIOS product (engine), the reduced-radix experiment and the FP64-pipe experiment (52-bit limbs
+    split exactly with DFMA, fq_fp64.cuh) agree with the oracle on edge values and random operands."""
     z = golden["field_vectors"]
     key = "c%d_f0" % modulus
     rng = np.random.default_rng(5 + modulus)
@@ -139,7 +139,7 @@ def test_emu_both_multipliers(emu, oracle, golden, modulus):
     a = np.concatenate([z[key + "_a"], po.ints_to_array([int.from_bytes(rng.bytes(100), "little") % p for _ in range(500)])])
     b = np.concatenate([z[key + "_b"], po.ints_to_array([int.from_bytes(rng.bytes(100), "little") % p for _ in range(500)])])
     want = oracle.field_op(modulus, 0, 0, a, b)
-    for which in (0, 1):
+    for which in (0, 1, 2):
         out = np.zeros_like(a)
         emu.emu_fq_mul(modulus, which, a.size // 12, _p(a), _p(b), _p(out))
         assert (out == want).all(), which
