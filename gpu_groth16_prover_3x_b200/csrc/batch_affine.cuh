@@ -335,6 +335,18 @@ __device__ __forceinline__ void prefetch_coord(const Team<F> &T, const uint32_t 
     prefetch_l2(p + NLIMB * 4 - 4);
 }
 
+#if B200_COOP_MOVES
+#define BA_G2S g2s_coop
+#define BA_S2G s2g_coop
+#define BA_G2S_BEGIN() g2s_coop_begin()
+#define BA_G2S_WAIT() g2s_coop_wait()
+#else
+#define BA_G2S g2s
+#define BA_S2G s2g
+#define BA_G2S_BEGIN()
+#define BA_G2S_WAIT()
+#endif
+
 template <class G, bool FIRST>
 __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch_add(BaArgs a) {
     typedef typename G::F F;
@@ -421,16 +433,20 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
                     async_wait<1>();
                 } else async_wait<0>();
             } else {
-                g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
-                g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
+                BA_G2S_BEGIN();
+                BA_G2S(T, s.X1, in + (size_t)r1 * AFFW, valid);
+                BA_G2S(T, s.X2, in + (size_t)r2 * AFFW, valid);
+                BA_G2S_WAIT();
             }
             const uint32_t code = pair_forward(T, s, valid, valid, [&](bool pred) {
-                g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, pred);
-                g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, pred);
+                BA_G2S_BEGIN();
+                BA_G2S(T, s.Y1, in + (size_t)r1 * AFFW + EW, pred);
+                BA_G2S(T, s.Y2, in + (size_t)r2 * AFFW + EW, pred);
+                BA_G2S_WAIT();
                 if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, pred); T.neg_if(s.Y2, s.Y2, d.y >> 31, pred); }
             });
             if (valid && T.comp == 0) a.out_inf[j] = (uint8_t)code;   // parked until the backward pass
-            s2g(T, a.out_pts + (size_t)j * AFFW, s.INV, valid);       // exclusive prefix, parked in the output slot
+            BA_S2G(T, a.out_pts + (size_t)j * AFFW, s.INV, valid);       // exclusive prefix, parked in the output slot
             T.mul(s.INV, s.INV, s.X2);
             if (C::PREFETCH) { int t = s.X1; s.X1 = NX1; NX1 = t; t = s.X2; s.X2 = NX2; NX2 = t; }
         }
@@ -487,16 +503,18 @@ __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch
                 }
                 res_inf = pair_backward_tail(T, s, code);
             } else {
-                g2s(T, s.X1, in + (size_t)r1 * AFFW, valid);
-                g2s(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);
-                g2s(T, s.X2, in + (size_t)r2 * AFFW, valid);
-                g2s(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
-                g2s(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
+                BA_G2S_BEGIN();
+                BA_G2S(T, s.X1, in + (size_t)r1 * AFFW, valid);
+                BA_G2S(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);
+                BA_G2S(T, s.X2, in + (size_t)r2 * AFFW, valid);
+                BA_G2S(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
+                BA_G2S(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
+                BA_G2S_WAIT();
                 if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, valid); T.neg_if(s.Y2, s.Y2, d.y >> 31, valid); }
                 res_inf = pair_backward(T, s, code);
             }
-            s2g(T, a.out_pts + (size_t)j * AFFW, s.X2, valid);
-            s2g(T, a.out_pts + (size_t)j * AFFW + EW, s.Y2, valid);
+            BA_S2G(T, a.out_pts + (size_t)j * AFFW, s.X2, valid);
+            BA_S2G(T, a.out_pts + (size_t)j * AFFW + EW, s.Y2, valid);
             if (valid && T.comp == 0) a.out_inf[j] = res_inf ? 1 : 0;
             if (C::PREFETCH) { int t = s.X1; s.X1 = NX1; NX1 = t; t = s.X2; s.X2 = NX2; NX2 = t; t = s.PRE; s.PRE = NPRE; NPRE = t; }
         }

@@ -104,6 +104,49 @@ __device__ __forceinline__ void s2g(const Team<F> &T, uint32_t *g, int slot, boo
         for (int q = 0; q < QUADS; ++q) dst[q] = src[q * LANES];
     }
 }
+// The same two movements done by the WARP for its 32 lanes together: lane l moves quad (k * 32 + l) % 6 of the
+// element of lane (k * 32 + l) / 6, k = 0..5, so that one LDG.128 / STG.128 covers the contiguous 96 bytes of five
+// or six elements (8-11 cache lines) instead of one 16-byte piece of each of 32 elements (32 lines, and every
+// 32-byte sector requested twice).  g is the lane's own element as for g2s / s2g.  Must be called by all 32 lanes.
+#ifndef B200_COOP_MOVES
+#define B200_COOP_MOVES 1
+#endif
+template <class F>
+__device__ __forceinline__ void g2s_coop(const Team<F> &T, int slot, const uint32_t *g, bool pred) {
+    // asynchronous (LDGSTS): issue any number of these, then g2s_coop_wait() once -- one round trip for all of them
+    const int lane = threadIdx.x & 31;
+    const unsigned long long mine = pred ? reinterpret_cast<unsigned long long>(g + T.comp * NLIMB) : 0ull;
+    uint4 *col0 = T.elem(slot, T.comp) - lane;
+#pragma unroll
+    for (int k = 0; k < QUADS; ++k) {
+        const int idx = k * 32 + lane, p = idx / QUADS, q = idx - p * QUADS;
+        const unsigned long long gp = __shfl_sync(0xffffffffu, mine, p);
+        if (gp != 0ull) {
+            const unsigned saddr = (unsigned)__cvta_generic_to_shared(col0 + q * LANES + p);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(reinterpret_cast<const uint4 *>(gp) + q) : "memory");
+        }
+    }
+}
+__device__ __forceinline__ void g2s_coop_begin() { __syncwarp(); }   // the lanes' earlier slab accesses are over
+__device__ __forceinline__ void g2s_coop_wait() {
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+}
+template <class F>
+__device__ __forceinline__ void s2g_coop(const Team<F> &T, uint32_t *g, int slot, bool pred) {
+    const int lane = threadIdx.x & 31;
+    const unsigned long long mine = pred ? reinterpret_cast<unsigned long long>(g + T.comp * NLIMB) : 0ull;
+    const uint4 *col0 = T.elem(slot, T.comp) - lane;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < QUADS; ++k) {
+        const int idx = k * 32 + lane, p = idx / QUADS, q = idx - p * QUADS;
+        const unsigned long long gp = __shfl_sync(0xffffffffu, mine, p);
+        if (gp != 0ull) reinterpret_cast<uint4 *>(gp)[q] = col0[q * LANES + p];
+    }
+    __syncwarp();
+}
 // asynchronous 128-bit global -> shared copies (LDGSTS)
 template <class F>
 __device__ __forceinline__ void g2s_async(const Team<F> &T, int slot, const uint32_t *g, bool pred) {

@@ -115,8 +115,8 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_synth_bases(uint32_
 template <class G>
 struct DblCfg {
     static constexpr int DEG = G::F::DEG;
-    static constexpr int TPB = DEG == 1 ? 4 : (DEG == 2 ? 2 : 1);
-    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 3 : 4);
+    static constexpr int TPB = 12 / DEG;     // one block of twelve warps per SM (see BaCfg, batch_affine.cuh)
+    static constexpr int MINB = 1;
     typedef TeamSetup<G, 6, TPB> TS;
 };
 template <class G>
