@@ -31,7 +31,10 @@
 namespace mnt753 {
 
 constexpr uint32_t BA_NONE = 0xffffffffu;
-constexpr int BA_BMAX = 256;  // additions per lane and tile
+#ifndef B200_BA_BMAX
+#define B200_BA_BMAX 2048
+#endif
+constexpr int BA_BMAX = B200_BA_BMAX;  // additions per lane and tile
 enum : uint32_t { BA_NORMAL = 0, BA_DBL = 1, BA_CANCEL = 2, BA_COPY1 = 3, BA_IDLE = 4 };
 
 // Six slab slots per team: the operands, the running inverse and one prefix/scratch.  The denominator
