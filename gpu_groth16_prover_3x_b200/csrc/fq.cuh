@@ -116,7 +116,7 @@ MSM_DEVICE void fq_mul_small(fq_t &r, const fq_t &a) {
     for (int i = 0; i < NLIMB; ++i) r[i] = acc[i];
 }
 
-// r = c * a as a plain integer (NOT reduced); c <= 13 and a < p < 2^753 so the result is < 2^757
+// r = c * a as a plain integer (NOT reduced); c <= 22 and a < p < 2^753 so the result is < 2^758
 // and still fits 24 limbs.  Used to fold the tower non-residue into one operand of a dot product.
 MSM_DEVICE void fq_scale_unreduced(fq_t &r, const fq_t &a, uint32_t c) {
     uint32_t hi[NLIMB];
