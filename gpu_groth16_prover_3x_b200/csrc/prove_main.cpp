@@ -39,10 +39,8 @@ int main(int argc, char **argv) {
     if (!input) { fprintf(stderr, "cannot allocate %zu bytes of pinned memory\n", input_bytes); return 3; }
     for (int rep = 0; rep < repeats; ++rep) {
         t = std::chrono::high_resolution_clock::now();
-        FILE *f = fopen(argv[4], "rb");
-        if (!f || fread(input, 1, input_bytes, f) != input_bytes) { fprintf(stderr, "cannot read %s (expected %zu bytes)\n", argv[4], input_bytes); return 2; }
-        fclose(f);
-        if (b200msm_prove(ctx, key, input, input_bytes, proof.data())) { fprintf(stderr, "%s\n", b200msm_last_error(ctx)); return 4; }
+        if (b200msm_prove_file(ctx, key, argv[4], input, proof.data())) { fprintf(stderr, "%s\n", b200msm_last_error(ctx)); return 4; }
+        FILE *f;
         f = fopen(argv[5], "wb");
         if (!f || fwrite(proof.data(), 1, proof.size(), f) != proof.size()) { fprintf(stderr, "cannot write %s\n", argv[5]); return 2; }
         fclose(f);

@@ -115,16 +115,12 @@ void b200msm_pinned_free(void *p) {
 size_t b200msm_proof_bytes(const b200msm_ctx *ctx) { return ctx ? (size_t)(2 * 192 + 192 * g2_deg(ctx)) : 0; }
 size_t b200msm_input_bytes(const b200msm_key *key) { return key ? ((key->m + 1) + 3 * (key->d + 1) + 1) * 96 : 0; }
 
-int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_image, size_t bytes, uint8_t *proof) {
-    if (!ctx) return B200MSM_ERR_ARG;
-    if (!key || !input_image || !proof) return fail(ctx, B200MSM_ERR_ARG, "null pointer");
-    const size_t d = key->d, m = key->m;
-    if (bytes != b200msm_input_bytes(key)) return fail(ctx, B200MSM_ERR_ARG, "input image of %zu bytes, expected %zu", bytes, b200msm_input_bytes(key));
-    // layout of <curve>-input (main.cpp:35-85): w[m+1], ca[d+1], cb[d+1], cc[d+1], r -- Fr, Montgomery limbs
-    const uint64_t *w = static_cast<const uint64_t *>(input_image);
-    const uint64_t *ca = w + (m + 1) * 12, *cb = ca + (d + 1) * 12, *cc = cb + (d + 1) * 12, *r = cc + (d + 1) * 12;
-    const int dg = g2_deg(ctx);
-    uint64_t A[36], rB1[36], B2[108], L[36], H[36];
+}  // extern "C"
+
+namespace {
+// First half of a proof: witness and r on the device, the four witness MSMs in flight.  Needs w and r only.
+int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, const uint64_t *r, uint64_t *A, uint64_t *rB1, uint64_t *B2, uint64_t *L) {
+    const size_t m = key->m;
     int rc;
     // The witness crosses PCIe once; the B1 query runs on r * w so that its result is the r * Bt1 term of C directly
     // (sum (r w_i) B1_i = r * sum w_i B1_i: the same group element, no 753-step scalar multiplication afterwards).
@@ -135,13 +131,23 @@ int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_im
     CU(cudaEventRecord(key->ready, key->stream));
     for (int l = 0; l < 4; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, key->ready, 0));
     const uint64_t *wd = reinterpret_cast<const uint64_t *>(key->w_dev), *rwd = reinterpret_cast<const uint64_t *>(key->rw_dev);
-    // the four witness MSMs in flight together (cuda_prover_piecewise.cu:162-167), the H polynomial beside them
+    // the four witness MSMs in flight together (cuda_prover_piecewise.cu:162-167)
     if ((rc = b200msm_msm_async(ctx, 0, key->slot[0], 0, wd, m + 1, A))) return rc;
     if ((rc = b200msm_msm_async(ctx, 1, key->slot[1], 0, rwd, m + 1, rB1))) return rc;
     if ((rc = b200msm_msm_async(ctx, 2, key->slot[2], 0, wd, m + 1, B2))) return rc;
     if ((rc = b200msm_msm_async(ctx, 3, key->slot[3], 0, wd + 2 * 12, m - 1, L))) return rc;   // w[2..m] (:167)
+    return B200MSM_OK;
+}
+void prove_drain(b200msm_ctx *ctx) { for (int l = 0; l < 4; ++l) b200msm_wait(ctx, l); }
+
+// Second half: the H polynomial beside the MSMs, the H query, the assembly and the proof bytes.
+int prove_finish(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc,
+                 uint64_t *A, uint64_t *rB1, uint64_t *B2, uint64_t *L, uint8_t *proof) {
+    const size_t d = key->d;
+    const int dg = g2_deg(ctx);
+    uint64_t H[36];
     const uint64_t *h_dev = nullptr;
-    rc = b200msm_compute_h(ctx, d, ca, cb, cc, nullptr, &h_dev);
+    int rc = b200msm_compute_h(ctx, d, ca, cb, cc, nullptr, &h_dev);
     int rcw = b200msm_wait(ctx, 0);
     if (rc || rcw) { for (int l = 1; l < 4; ++l) b200msm_wait(ctx, l); return rc ? rc : rcw; }
     rc = b200msm_msm_async(ctx, 0, key->slot[4], 0, h_dev, d, H);
@@ -163,6 +169,49 @@ int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_im
     memcpy(proof + 192, b_aff, (size_t)192 * dg);
     memcpy(proof + 192 + 192 * dg, c_aff, 192);
     return B200MSM_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_image, size_t bytes, uint8_t *proof) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!key || !input_image || !proof) return fail(ctx, B200MSM_ERR_ARG, "null pointer");
+    const size_t d = key->d, m = key->m;
+    if (bytes != b200msm_input_bytes(key)) return fail(ctx, B200MSM_ERR_ARG, "input image of %zu bytes, expected %zu", bytes, b200msm_input_bytes(key));
+    // layout of <curve>-input (main.cpp:35-85): w[m+1], ca[d+1], cb[d+1], cc[d+1], r -- Fr, Montgomery limbs
+    const uint64_t *w = static_cast<const uint64_t *>(input_image);
+    const uint64_t *ca = w + (m + 1) * 12, *cb = ca + (d + 1) * 12, *cc = cb + (d + 1) * 12, *r = cc + (d + 1) * 12;
+    uint64_t A[36], rB1[36], B2[108], L[36];
+    int rc = prove_begin(ctx, key, w, r, A, rB1, B2, L);
+    if (rc) { prove_drain(ctx); return rc; }
+    return prove_finish(ctx, key, ca, cb, cc, A, rB1, B2, L, proof);
+}
+
+// The same proof straight from the reference's <curve>-input FILE: r (the last 96 bytes) and the witness are read
+// first and the four witness MSMs start; the three coefficient vectors of the H polynomial (three quarters of the
+// file) are read while the GPU works.  `buffer` is host scratch of b200msm_input_bytes() bytes (pinned for full-rate
+// uploads: b200msm_pinned_alloc); it holds the file image afterwards.
+int b200msm_prove_file(b200msm_ctx *ctx, const b200msm_key *key, const char *input_path, void *buffer, uint8_t *proof) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (!key || !input_path || !buffer || !proof) return fail(ctx, B200MSM_ERR_ARG, "null pointer");
+    const size_t d = key->d, m = key->m, bytes = b200msm_input_bytes(key);
+    FILE *f = fopen(input_path, "rb");
+    if (!f) return fail(ctx, B200MSM_ERR_ARG, "cannot open %s", input_path);
+    char *img = static_cast<char *>(buffer);
+    const size_t w_bytes = (m + 1) * 96, h_bytes = 3 * (d + 1) * 96;
+    bool ok = fseek(f, 0, SEEK_END) == 0 && (size_t)ftell(f) == bytes;
+    ok = ok && fseek(f, (long)(bytes - 96), SEEK_SET) == 0 && fread(img + bytes - 96, 1, 96, f) == 96;
+    ok = ok && fseek(f, 0, SEEK_SET) == 0 && fread(img, 1, w_bytes, f) == w_bytes;
+    if (!ok) { fclose(f); return fail(ctx, B200MSM_ERR_ARG, "%s is not an input file of %zu bytes for this key", input_path, bytes); }
+    uint64_t *w = reinterpret_cast<uint64_t *>(img);
+    const uint64_t *ca = w + (m + 1) * 12, *cb = ca + (d + 1) * 12, *cc = cb + (d + 1) * 12, *r = cc + (d + 1) * 12;
+    uint64_t A[36], rB1[36], B2[108], L[36];
+    int rc = prove_begin(ctx, key, w, r, A, rB1, B2, L);
+    if (!rc && fread(img + w_bytes, 1, h_bytes, f) != h_bytes) rc = fail(ctx, B200MSM_ERR_ARG, "short read of %s", input_path);
+    fclose(f);
+    if (rc) { prove_drain(ctx); return rc; }
+    return prove_finish(ctx, key, ca, cb, cc, A, rB1, B2, L, proof);
 }
 
 }  // extern "C"

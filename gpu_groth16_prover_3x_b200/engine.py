@@ -76,6 +76,7 @@ def load_library():
     lib.b200msm_input_bytes.argtypes = [vp]
     lib.b200msm_input_bytes.restype = sz
     lib.b200msm_prove.argtypes = [vp, vp, vp, sz, vp]
+    lib.b200msm_prove_file.argtypes = [vp, vp, ctypes.c_char_p, vp, vp]
     lib.b200msm_pinned_alloc.argtypes = [sz]
     lib.b200msm_pinned_alloc.restype = vp
     lib.b200msm_pinned_free.argtypes = [vp]
@@ -300,6 +301,19 @@ class MsmContext:
         buf = np.frombuffer(input_image, dtype=np.uint8) if isinstance(input_image, (bytes, bytearray)) else np.ascontiguousarray(input_image).view(np.uint8)
         proof = np.zeros(self.lib.b200msm_proof_bytes(self._h), np.uint8)
         self._check(self.lib.b200msm_prove(self._h, key, _ptr(buf), buf.size, _ptr(proof)))
+        return proof.tobytes()
+
+    def prove_file(self, key, input_path):
+        """The same from the <curve>-input file: the witness MSMs start while the rest of the file is still being read."""
+        n = self.lib.b200msm_input_bytes(key)
+        buf = self.lib.b200msm_pinned_alloc(n)
+        if not buf:
+            raise MsmError("cannot allocate %d bytes of pinned memory" % n)
+        try:
+            proof = np.zeros(self.lib.b200msm_proof_bytes(self._h), np.uint8)
+            self._check(self.lib.b200msm_prove_file(self._h, key, input_path.encode(), buf, _ptr(proof)))
+        finally:
+            self.lib.b200msm_pinned_free(buf)
         return proof.tobytes()
 
     def compute_h(self, ca, cb, cc, to_host=True):

@@ -130,6 +130,11 @@ void b200msm_key_free(b200msm_ctx *ctx, b200msm_key *key);
 size_t b200msm_proof_bytes(const b200msm_ctx *ctx);
 size_t b200msm_input_bytes(const b200msm_key *key);
 int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_image, size_t bytes, uint8_t *proof);
+/* The same from the <curve>-input FILE (what run_prover does with load_scalars / B::read_input,
+ * cuda_prover_piecewise.cu:151-155): r and the witness are read first, the four witness MSMs start, and the
+ * coefficient vectors of the H polynomial (three quarters of the file) are read while the GPU works.
+ * `buffer`: host scratch of b200msm_input_bytes() bytes (b200msm_pinned_alloc for full-rate uploads). */
+int b200msm_prove_file(b200msm_ctx *ctx, const b200msm_key *key, const char *input_path, void *buffer, uint8_t *proof);
 /* Page-locked host memory for witness / scalar buffers (H2D at full PCIe rate, truly asynchronous uploads);
  * plain malloc'ed memory works everywhere too, only slower.  NULL on failure. */
 void *b200msm_pinned_alloc(size_t bytes);

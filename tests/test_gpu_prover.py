@@ -69,6 +69,9 @@ def test_whole_proof_through_the_c_abi(fast_params, curve):
         assert ctx.prove(key, image) == want           # a resident key proves again
         with pytest.raises(pkg.MsmError):
             ctx.prove(key, image[:-96])                # truncated witness
+        assert ctx.prove_file(key, inp) == want        # input read from the file while the witness MSMs run
+        with pytest.raises(pkg.MsmError):
+            ctx.prove_file(key, params)                # a file of the wrong size
         ctx.free_key(key)
         with pytest.raises(pkg.MsmError):
             ctx.load_key(open(params, "rb").read()[:-8])
