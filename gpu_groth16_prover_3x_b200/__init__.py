@@ -6,7 +6,7 @@ The compute path is hand-written CUDA for sm_100a behind the C ABI of include/b2
 fallback and raises if the CUDA library is missing.
 """
 from .engine import (G1, G2, MNT4753, MNT6753, MsmContext, MsmError, degree, library_path, load_library,
-                     shard_ranges)
+                     prove_sharded, shard_ranges)
 
 __all__ = ["G1", "G2", "MNT4753", "MNT6753", "MsmContext", "MsmError", "degree", "library_path", "load_library",
-           "shard_ranges"]
+           "prove_sharded", "shard_ranges"]

@@ -77,6 +77,9 @@ def load_library():
     lib.b200msm_input_bytes.restype = sz
     lib.b200msm_prove.argtypes = [vp, vp, vp, sz, vp]
     lib.b200msm_prove_file.argtypes = [vp, vp, ctypes.c_char_p, vp, vp]
+    lib.b200msm_key_load_shard.argtypes = [vp, vp, sz, ci, ci, ctypes.POINTER(vp)]
+    lib.b200msm_prove_sharded.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ci, vp, sz, vp]
+    lib.b200msm_prove_sharded_file.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ctypes.c_char_p, vp, vp]
     lib.b200msm_pinned_alloc.argtypes = [sz]
     lib.b200msm_pinned_alloc.restype = vp
     lib.b200msm_pinned_free.argtypes = [vp]
@@ -303,6 +306,13 @@ class MsmContext:
         self._check(self.lib.b200msm_prove(self._h, key, _ptr(buf), buf.size, _ptr(proof)))
         return proof.tobytes()
 
+    def load_key_shard(self, params, shard, nshards):
+        """Shard `shard` of `nshards` (point range of every query) of a <curve>-parameters image (bytes / numpy uint8)."""
+        key = ctypes.c_void_p()
+        buf = np.frombuffer(params, dtype=np.uint8) if isinstance(params, (bytes, bytearray)) else np.ascontiguousarray(params).view(np.uint8)
+        self._check(self.lib.b200msm_key_load_shard(self._h, _ptr(buf), buf.size, shard, nshards, ctypes.byref(key)))
+        return key
+
     def prove_file(self, key, input_path):
         """The same from the <curve>-input file: the witness MSMs start while the rest of the file is still being read."""
         n = self.lib.b200msm_input_bytes(key)
@@ -372,3 +382,15 @@ class MsmContext:
             flags = np.ascontiguousarray(flags, dtype=np.uint32)
         self._check(self.lib.b200msm_selftest_point(self._h, group, op, n, acc.ctypes.data, _ptr(q), _ptr(flags), out.ctypes.data))
         return out
+
+
+def prove_sharded(ctxs, keys, input_image):
+    """One proof over several contexts (one per GPU; ctxs[g] / keys[g] = shard g): b200msm_prove_sharded."""
+    n = len(ctxs)
+    lib = ctxs[0].lib
+    buf = np.frombuffer(input_image, dtype=np.uint8) if isinstance(input_image, (bytes, bytearray)) else np.ascontiguousarray(input_image).view(np.uint8)
+    proof = np.zeros(lib.b200msm_proof_bytes(ctxs[0]._h), np.uint8)
+    ca = (ctypes.c_void_p * n)(*[c._h for c in ctxs])
+    ka = (ctypes.c_void_p * n)(*[k for k in keys])
+    ctxs[0]._check(lib.b200msm_prove_sharded(ca, ka, n, _ptr(buf), buf.size, _ptr(proof)))
+    return proof.tobytes()

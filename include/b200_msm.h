@@ -135,6 +135,16 @@ int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_im
  * coefficient vectors of the H polynomial (three quarters of the file) are read while the GPU works.
  * `buffer`: host scratch of b200msm_input_bytes() bytes (b200msm_pinned_alloc for full-rate uploads). */
 int b200msm_prove_file(b200msm_ctx *ctx, const b200msm_key *key, const char *input_path, void *buffer, uint8_t *proof);
+/* The same over several GPUs of one box (the reference has no multi-GPU path): every query is split by
+ * point range, shard g of n (a context on its own GPU and the key shard loaded into it) runs its five MSMs on its
+ * slice of the witness, the H polynomial is computed on shard 0's GPU and its coefficients reach the other shards by
+ * peer copy, the 5 n partial points are folded on shard 0's GPU.  No collective; ctxs[g] / keys[g] must be shard g of n
+ * of the same parameter image.  Contexts may share a device (tests). */
+int b200msm_key_load_shard(b200msm_ctx *ctx, const void *params_image, size_t bytes, int shard, int nshards, b200msm_key **key);
+int b200msm_prove_sharded(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int nshards, const void *input_image, size_t bytes,
+                          uint8_t *proof);
+int b200msm_prove_sharded_file(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int nshards, const char *input_path, void *buffer,
+                               uint8_t *proof);
 /* Page-locked host memory for witness / scalar buffers (H2D at full PCIe rate, truly asynchronous uploads);
  * plain malloc'ed memory works everywhere too, only slower.  NULL on failure. */
 void *b200msm_pinned_alloc(size_t bytes);

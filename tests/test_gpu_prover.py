@@ -82,6 +82,43 @@ def test_whole_proof_through_the_c_abi(fast_params, curve):
     assert sha256(os.path.join(d, curve + "-output-cli")) == hashlib.sha256(want).hexdigest()
 
 
+@pytest.mark.parametrize("nshards", [2, 3])
+def test_sharded_proof_through_the_c_abi(fast_params, nshards):
+    """b200msm_key_load_shard + b200msm_prove_sharded[_file]: every query split by point range over `nshards` contexts
+    (one per GPU where the box has that many, else several on one GPU -- the sharding logic is the same), H on shard 0,
+    its coefficients handed on by peer copy, partial points folded: same proof bytes as the reference CPU prover."""
+    import torch
+    import gpu_groth16_prover_3x_b200 as pkg
+    d = fast_params
+    for curve in ("MNT4753", "MNT6753"):
+        params, inp = os.path.join(d, "%s-parameters" % curve), os.path.join(d, "%s-input" % curve)
+        ref_out = os.path.join(d, curve + "-output-ref")
+        if not os.path.exists(ref_out):
+            subprocess.run([BINS[1], curve, "compute", params, inp, ref_out], cwd=d, check=True, stdout=subprocess.DEVNULL, timeout=1800)
+        want = open(ref_out, "rb").read()
+        ndev = torch.cuda.device_count()
+        cid = pkg.MNT4753 if curve == "MNT4753" else pkg.MNT6753
+        ctxs = [pkg.MsmContext(cid, g % ndev) for g in range(nshards)]
+        try:
+            image = open(params, "rb").read()
+            keys = [c.load_key_shard(image, g, nshards) for g, c in enumerate(ctxs)]
+            assert pkg.prove_sharded(ctxs, keys, open(inp, "rb").read()) == want
+            with pytest.raises(pkg.MsmError):
+                pkg.prove_sharded(ctxs[::-1], keys[::-1], open(inp, "rb").read())   # shards out of order
+            for c, k in zip(ctxs, keys):
+                c.free_key(k)
+        finally:
+            for c in ctxs:
+                c.close()
+    if torch.cuda.device_count() >= nshards:      # the command-line prover on real devices
+        curve = "MNT4753"
+        cli = os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "b200_prove")
+        out = os.path.join(d, curve + "-output-cli%d" % nshards)
+        subprocess.run([cli, curve, "compute", os.path.join(d, curve + "-parameters"), os.path.join(d, curve + "-input"), out, "1", str(nshards)],
+                       check=True, stdout=subprocess.DEVNULL, timeout=900)
+        assert sha256(out) == sha256(os.path.join(d, curve + "-output-ref"))
+
+
 def test_sharded_prover_two_gpus(fast_params):
     """Every query sharded by point range over two GPUs, partial points folded: same proof."""
     import torch
