@@ -273,6 +273,16 @@ int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size
     return ops_for(ctx->curve, group).fold(ctx, partials_xyz, n, out_xyz);
 }
 
+int b200msm_shard_range(size_t n, int shard, int nshards, size_t *offset, size_t *length) {
+    if (nshards < 1 || shard < 0 || shard >= nshards || !offset || !length) return B200MSM_ERR_ARG;
+    // 128-bit product: n * nshards cannot overflow for any n a base set can hold, but the ABI takes size_t
+    const unsigned __int128 N = n;
+    const size_t lo = (size_t)(N * (unsigned)shard / (unsigned)nshards), hi = (size_t)(N * (unsigned)(shard + 1) / (unsigned)nshards);
+    *offset = lo;
+    *length = hi - lo;
+    return B200MSM_OK;
+}
+
 int b200msm_to_affine(b200msm_ctx *ctx, int group, size_t n, const uint64_t *xyz, uint64_t *out_affine) {
     if (!ctx) return B200MSM_ERR_ARG;
     if (!xyz || !out_affine || n == 0 || n > (1u << 24) || (group != B200MSM_G1 && group != B200MSM_G2))

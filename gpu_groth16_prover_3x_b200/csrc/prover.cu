@@ -69,8 +69,7 @@ int b200msm_key_load_shard(b200msm_ctx *ctx, const void *params_image, size_t by
     const size_t count[5] = {m + 1, m + 1, m + 1, m - 1, d}, words[5] = {g1, g1, g2, g1, g1};
     for (int q = 0; q < 5; ++q) {
         // point-range sharding: shard g of G owns [N g / G, N (g + 1) / G) of every query
-        key->lo[q] = count[q] * (size_t)shard / (size_t)nshards;
-        key->cnt[q] = count[q] * (size_t)(shard + 1) / (size_t)nshards - key->lo[q];
+        b200msm_shard_range(count[q], shard, nshards, &key->lo[q], &key->cnt[q]);
         int rc = b200msm_bases_upload(ctx, group[q], p + key->lo[q] * words[q], key->cnt[q], &key->slot[q]);
         if (rc) { b200msm_key_free(ctx, key); return rc; }
         p += count[q] * words[q];

@@ -61,6 +61,7 @@ def load_library():
     lib.b200msm_bases_download.argtypes = [vp, ci, sz, sz, vp]
     lib.b200msm_to_affine.argtypes = [vp, ci, sz, vp, vp]
     lib.b200msm_fold.argtypes = [vp, ci, vp, sz, vp]
+    lib.b200msm_shard_range.argtypes = [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     lib.b200msm_set_stream.argtypes = [vp, ci, vp]
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
     lib.b200msm_set_table_budget.argtypes = [vp, sz]
@@ -99,15 +100,12 @@ def load_library():
 
 
 def shard_ranges(n, parts):
-    """Point-range sharding of an MSM of n points over `parts` GPUs: contiguous,
-    sizes differ by at most one, in order.  -> list of (offset, length)."""
-    base, extra = divmod(n, parts)
-    out, off = [], 0
-    for i in range(parts):
-        ln = base + (1 if i < extra else 0)
-        out.append((off, ln))
-        off += ln
-    return out
+    """Point-range sharding of an MSM of n points over `parts` GPUs: shard g owns
+    [n g / parts, n (g + 1) / parts) -- the rule of b200msm_shard_range (include/b200_msm.h), which
+    b200msm_key_load_shard uses as well (tests/test_abi.py asserts the two agree).  -> list of (offset, length)."""
+    if parts < 1:
+        raise ValueError("parts must be >= 1")
+    return [(n * g // parts, n * (g + 1) // parts - n * g // parts) for g in range(parts)]
 
 
 def _ptr(x):
@@ -241,13 +239,6 @@ class MsmContext:
         self._check(self.lib.b200msm_ec_reduce(self._h, group, _ptr(bases_affine), _ptr(scalars), n, out.ctypes.data))
         return out
 
-    # names of the reference's plugin API (prover_reference_functions.hpp:59-62)
-    def multiexp_G1(self, scalars, bases_affine, length=None):
-        return self.ec_reduce(G1, bases_affine, scalars, length)
-
-    def multiexp_G2(self, scalars, bases_affine, length=None):
-        return self.ec_reduce(G2, bases_affine, scalars, length)
-
     def fold(self, group, partials_xyz):
         """Sum of Jacobian partial results (one per GPU shard) -> one Jacobian point, on this GPU."""
         per = 36 * degree(self.curve, group)
@@ -318,7 +309,7 @@ class MsmContext:
         n = self.lib.b200msm_input_bytes(key)
         buf = self.lib.b200msm_pinned_alloc(n)
         if not buf:
-            raise MsmError("cannot allocate %d bytes of pinned memory" % n)
+            raise MsmError(3, "cannot allocate %d bytes of pinned memory" % n)
         try:
             proof = np.zeros(self.lib.b200msm_proof_bytes(self._h), np.uint8)
             self._check(self.lib.b200msm_prove_file(self._h, key, input_path.encode(), buf, _ptr(proof)))

@@ -94,6 +94,10 @@ int b200msm_to_affine(b200msm_ctx *ctx, int group, size_t n, const uint64_t *xyz
  * point); this folds n partials into one point on this context's GPU.  The reference has no
  * multi-GPU path; inside the reference the same fold is G - 1 libff additions after read_pt_*. */
 int b200msm_fold(b200msm_ctx *ctx, int group, const uint64_t *partials_xyz, size_t n, uint64_t *out_xyz);
+/* THE point-range sharding rule, used by b200msm_key_load_shard and to be used by every caller that
+ * shards on its own: shard g of G of an n-point query owns [n g / G, n (g + 1) / G) (integer division).  Pure host
+ * arithmetic, no context.  Returns B200MSM_ERR_ARG for nshards < 1 or shard outside [0, nshards). */
+int b200msm_shard_range(size_t n, int shard, int nshards, size_t *offset, size_t *length);
 
 /* The H-polynomial of the prover on the device: coefficients_for_H = compute_H(d, ca, cb, cc)
  * (cuda_prover_piecewise.cu:14-49), i.e. the three inverse FFTs, three coset FFTs, the pointwise

@@ -27,9 +27,7 @@
 #include <string>
 #include <vector>
 
-#include "libsnark/prover_reference_functions.cpp"  // the reference TU itself (see above)
-
-#include "b200_msm.h"
+#include "b200_bundle.hpp"  // #includes the reference TU itself (see above) and include/b200_msm.h
 
 // pinned host memory for the witness file (only cudaHostAlloc / cudaFreeHost of the CUDA runtime are used here;
 // declared by hand so that the harness does not need the CUDA headers)
@@ -41,9 +39,7 @@ namespace {
 typedef std::chrono::high_resolution_clock Clock;
 double ms_since(Clock::time_point t) { return std::chrono::duration<double, std::milli>(Clock::now() - t).count(); }
 
-template <class B> struct CurveOf;
-template <> struct CurveOf<mnt4753_libsnark> { static constexpr int id = B200MSM_MNT4753, deg2 = 2; };
-template <> struct CurveOf<mnt6753_libsnark> { static constexpr int id = B200MSM_MNT6753, deg2 = 3; };
+using b200::CurveOf;
 
 std::vector<char> slurp(const char *path) {
     FILE *f = fopen(path, "rb");
@@ -63,25 +59,7 @@ std::vector<char> slurp(const char *path) {
         if (rc_) { fprintf(stderr, "%s: %s\n", #call, b200msm_last_error(ctx)); abort(); } \
     } while (0)
 
-// the same seven FFTs as compute_H (cuda_prover_piecewise.cu:14-49), through the reference's own functions
-template <class B>
-typename B::vector_Fr *compute_H(size_t d, typename B::vector_Fr *ca, typename B::vector_Fr *cb, typename B::vector_Fr *cc) {
-    auto domain = B::get_evaluation_domain(d + 1);
-    B::domain_iFFT(domain, ca);
-    B::domain_iFFT(domain, cb);
-    B::domain_cosetFFT(domain, ca);
-    B::domain_cosetFFT(domain, cb);
-    size_t m = B::domain_get_m(domain);
-    B::vector_Fr_muleq(ca, cb, m);
-    B::domain_iFFT(domain, cc);
-    B::domain_cosetFFT(domain, cc);
-    B::vector_Fr_subeq(ca, cc, m);
-    B::domain_divide_by_Z_on_coset(domain, ca);
-    B::domain_icosetFFT(domain, ca);
-    typename B::vector_Fr *res = B::vector_Fr_zeros(m + 1);
-    B::vector_Fr_copy_into(ca, res, m);
-    return res;
-}
+using b200::compute_H;   // the seven FFTs of cuda_prover_piecewise.cu:14-49 through the bundle (b200_bundle.hpp)
 
 struct Query {
     int group;
@@ -121,13 +99,11 @@ int run(const char *params_path, const char *input_path, const char *output_path
         Q.slot.resize(n_gpus);
         Q.range.resize(n_gpus);
         Q.partial.assign((size_t)n_gpus * 36 * (Q.group == B200MSM_G1 ? 1 : C::deg2), 0);
-        const size_t base = Q.n / n_gpus, extra = Q.n % n_gpus;
-        size_t off = 0;
         for (int g = 0; g < n_gpus; ++g) {
-            const size_t len = base + ((size_t)g < extra ? 1 : 0);
+            size_t off = 0, len = 0;
+            b200msm_shard_range(Q.n, g, n_gpus, &off, &len);   // the one sharding rule of the ABI
             Q.range[g] = {off, len};
             CHECK(ctx[g], b200msm_bases_upload(ctx[g], Q.group, Q.bases + off * Q.point_words, len, &Q.slot[g]));
-            off += len;
         }
     }
     printf("upload + window tables: %.1f ms\n", ms_since(t));

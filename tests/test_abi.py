@@ -45,6 +45,25 @@ def test_shard_ranges():
             assert max(l for _, l in r) - min(l for _, l in r) <= 1
 
 
+def test_shard_rule_is_the_abis(engine_lib):
+    """engine.shard_ranges (python callers) and b200msm_shard_range (the C ABI, which b200msm_key_load_shard
+    uses) are one rule: a caller that mixes sharded keys with python-side ranges stays aligned."""
+    off, ln = ctypes.c_size_t(), ctypes.c_size_t()
+    for n in (0, 1, 7, 9, 1000, (1 << 20) - 1, (1 << 20) + 1, (1 << 24) + 5):
+        for parts in (1, 2, 3, 4, 5, 8):
+            want = pkg.shard_ranges(n, parts)
+            for g in range(parts):
+                assert engine_lib.b200msm_shard_range(n, g, parts, ctypes.byref(off), ctypes.byref(ln)) == 0
+                assert (off.value, ln.value) == want[g]
+    assert engine_lib.b200msm_shard_range(8, 2, 2, ctypes.byref(off), ctypes.byref(ln)) == 1
+    assert engine_lib.b200msm_shard_range(8, 0, 0, ctypes.byref(off), ctypes.byref(ln)) == 1
+
+
+def test_msm_error_carries_code():
+    e = pkg.MsmError(3, "cannot allocate")
+    assert e.code == 3 and "out of device memory" in str(e)
+
+
 def test_create_fails_loudly_without_gpu(engine_lib):
     import torch
     if torch.cuda.is_available():

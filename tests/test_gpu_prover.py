@@ -13,6 +13,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF = os.path.join(ROOT, "oracle", "_ref")
 BINS = [os.path.join(REF, b) for b in ("generate_parameters", "main", "b200_prover")]
+BUNDLE = os.path.join(REF, "b200_bundle_prover")
 
 
 def sha256(path):
@@ -46,6 +47,34 @@ def test_proof_sha256_equals_reference_cpu_prover(fast_params, curve):
         b = os.path.join(d, name)
         assert os.path.getsize(ref_out) == os.path.getsize(b) == (768 if curve == "MNT4753" else 960)
         assert sha256(ref_out) == sha256(b), extra
+
+
+@pytest.mark.parametrize("curve", ["MNT4753", "MNT6753"])
+def test_bundle_multiexp_adaptor(fast_params, curve):
+    """the reference's prover call sequence written against the plugin bundle only
+    (tests/integration/b200_bundle_prover.cpp), with B = b200_bundle<...> whose B::multiexp_G1 / multiexp_G2
+    (prover_reference_functions.cpp:350-368,690-708) run on the engine: libff projective vectors marshalled to the
+    affine wire format (Z == 0 -> y = 0), base sets cached per vector, results imported by B::read_pt_ECp/ECpe.
+    All five multiexps of a proof go through the two bundle functions; the proof must equal `main`'s byte for byte,
+    on one GPU, over two and three point-range shards (one per GPU where the box has them), and on a second proof
+    (cache hits only)."""
+    import re
+    if not os.path.exists(BUNDLE):
+        pytest.skip("oracle/_ref/b200_bundle_prover not built")
+    d = fast_params
+    params, inp = "%s-parameters" % curve, "%s-input" % curve
+    ref_out = os.path.join(d, curve + "-output-ref")
+    if not os.path.exists(ref_out):
+        subprocess.run([BINS[1], curve, "compute", params, inp, curve + "-output-ref"], cwd=d, check=True,
+                       stdout=subprocess.DEVNULL, timeout=1800)
+    for gpus in (1, 2, 3):
+        name = curve + "-output-bundle%d" % gpus
+        out = subprocess.run([BUNDLE, curve, "compute", params, inp, name, str(gpus), "b200", "2"], cwd=d, check=True,
+                             capture_output=True, text=True, timeout=900).stdout
+        print(out)
+        assert sha256(ref_out) == sha256(os.path.join(d, name)), gpus
+        m = re.search(r"base-set uploads: (\d+), cache hits: (\d+)", out)
+        assert m and (int(m.group(1)), int(m.group(2))) == (5, 5)   # second proof: no upload, no table build
 
 
 @pytest.mark.parametrize("curve", ["MNT4753", "MNT6753"])
