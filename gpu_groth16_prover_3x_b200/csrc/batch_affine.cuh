@@ -1,11 +1,11 @@
-// Batched-affine bucket accumulation (replaces the per-lane Jacobian chains of k_accumulate and the
-// edge fold; the reference's counterpart is the Straus kernel + pairwise tree, multiexp/reduce.cu:11-127).
+// Batched-affine bucket accumulation (the reference's counterpart is the Straus kernel + pairwise tree,
+// multiexp/reduce.cu:11-127).
 //
 // The sorted list of (bucket, point) entries is reduced by ROUNDS of pairwise AFFINE additions:
 // a bucket holding k points holds ceil(k/2) after a round, so every bucket is down to one point after
-// ceil(log2(max occupancy)) rounds and the total number of additions is the same sum_b (k_b - 1) as a
-// serial chain.  An affine addition costs one field inversion; Montgomery's simultaneous inversion
-// shares ONE inversion among all the additions of a tile (32 lanes x B additions):
+// ceil(log2 k) rounds and the total number of additions is the same sum_b (k_b - 1) as a serial chain.
+// An affine addition costs one field inversion; Montgomery's simultaneous inversion shares ONE
+// inversion among all the additions of a tile (32 lanes x B additions):
 //
 //   forward   d_i = x2 - x1 (or 2 y1 when doubling, 1 when there is nothing to add);  prefix products
 //   tile      product over the 32 lanes (xor butterfly), one binary-gcd inversion by one thread,
@@ -16,11 +16,16 @@
 // (8M + 3S) for the Jacobian mixed addition.  Prefix products are parked in the x-half of the output
 // slot of the same addition, so the round needs no scratch of its own.
 //
-// Per round r:   k_scan_halve* (next offsets = scan of ceil(k/2))  ->  k_plan (source rows of every
-// output point; binary search of its bucket)  ->  k_batch_add (the additions, persistent tiles).
-// Round 0 reads the window tables through the sorted entry list (row | sign << 31); later rounds read
-// the previous round's output.  Rounds after the last useful one exit on a device-side flag, so the host
-// enqueues a fixed worst-case number of rounds without ever synchronising.
+// TEAM-LOCAL ROUNDS (round 2 of the build; round 1 ran every round as five launches over the whole list):
+// the sorted list is cut into U contiguous ranges of about E / U entries, one per team (a team = DEG warps
+// = 32 lanes), at bucket boundaries -- only a bucket larger than half a team's share is split, its pieces
+// being summed afterwards by k_ba_fixup.  Each team then takes ITS buckets through all their rounds inside
+// ONE persistent launch (k_batch_add): per round it plans its pairs (lane per bucket: pair descriptors,
+// odd-one-out carried over), runs forward / inversion / backward over them, and rewrites its part of a
+// ping-pong list of point REFERENCES (table row | sign, or scratch slot, or infinity).  No grid-wide
+// synchronisation, no per-round scan / plan launches, and a round's fixed cost (the tile inversion) is hidden
+// behind the other teams of the SM instead of idling the GPU.  When all teams are done every bucket is one
+// reference in bucket_ref[], which the bucket reduction reads.
 #pragma once
 #ifdef MNT753_HOST_EMU
 #include "curves.cuh"
@@ -131,201 +136,128 @@ MSM_DEVICE void tile_inverse(const Team<F> &T, int INV, int S, int A, int B, int
 
 #ifndef MNT753_HOST_EMU
 // ------------------------------------------------------------------------------------------------
+// point references
+constexpr uint32_t REF_INF = 0xffffffffu;      // infinity / empty bucket / idle pair
+constexpr uint32_t REF_NEG = 0x80000000u;      // table reference: add the NEGATED point
+constexpr uint32_t REF_SCRATCH = 0x40000000u;  // index into the scratch point array, else a table row
+constexpr uint32_t REF_IDX = 0x3fffffffu;
+constexpr int BA_CTL_WORDS = 40;               // [0] rounds (max over teams) [1] largest bucket [2] additions [4 + r] pairs of round r
+
 struct BaArgs {
     uint32_t K;                 // buckets (all sets)
-    uint32_t round;
-    const uint32_t *off_cur;    // K + 1 offsets of the round's input list
-    uint32_t *off_next;         // K + 1 offsets of its output list
-    const uint32_t *entries;    // round 0: sorted (row | sign << 31)
-    const uint32_t *bases;      // round 0: window tables
-    const uint32_t *in_pts;     // round > 0: previous output (affine AoS)
-    const uint8_t *in_inf;
-    uint32_t *out_pts;
-    uint8_t *out_inf;
-    uint4 *pairs;               // the round's additions: (source 0, source 1, output index, -)
-    uint32_t *npairs;           // [rounds]
-    uint32_t *maxcnt;           // [rounds + 1] largest bucket occupancy entering each round
-    uint32_t *tile_counter;     // [rounds]
-    uint32_t *nrounds;          // rounds actually executed
-    uint32_t *bsum;             // scan scratch
-    uint32_t nscan;
+    uint32_t U;                 // teams that take a share of the list
+    uint32_t T;                 // entries per share = ceil(E / U), set by the kernels from the list's real length
+    const uint32_t *offs;       // K + 1 bucket offsets into the sorted list (offs[K] = E)
+    uint32_t *refs[2];          // ping-pong reference lists, E entries each; refs[0] = the sorted entries
+    const uint32_t *bases;      // window tables (affine AoS)
+    uint32_t *scratch;          // sums: region A (even rounds) at [0, capA), region B (odd rounds) at [capA, capA + capB)
+    uint32_t capA;
+    uint4 *pairs;               // a team's additions of the current round: (source 0, source 1, scratch slot, list slot)
+    uint8_t *codes;             // classification of each addition, parked between the two passes
+    uint32_t *cntv;             // K + U: points left in each piece (a bucket, or the part of a split bucket in one share)
+    uint32_t *bucket_ref;       // K: what is left of every bucket (preset to REF_INF by the host)
+    uint32_t *bnd_ref;          // 2 U: pieces of split buckets, at most two per share (first / last bucket of the share)
+    uint32_t *bnd_bucket;       //      their bucket ids (preset to REF_INF by the host)
+    uint32_t *ctl;              // BA_CTL_WORDS statistics
+    // k_ba_fixup only: the compacted pieces as a list of their own
+    uint32_t *fx_refs[2];       // 2 U each
+    uint32_t *fx_offs;          // 2 U + 1
+    uint32_t *fx_cntv;          // 2 U + 1
+    uint32_t *fx_bucket;        // 2 U
+    uint32_t fx_scratch_base;   // first scratch slot of the fix-up's own A / B regions
 };
 
-__device__ __forceinline__ bool ba_round_active(const BaArgs &a) { return a.round == 0 || a.maxcnt[a.round] > 1u; }
+// One share of a sorted list as seen by the team that owns it.
+struct BaView {
+    const uint32_t *offs;       // bucket offsets of the list
+    uint32_t E0, E1;            // the share: list entries [E0, E1)
+    uint32_t b0, npieces;       // its buckets b0 .. b0 + npieces - 1 (first and last possibly cut by E0 / E1)
+    uint32_t id;                // added to the bucket id wherever pieces of one bucket in different shares must not collide
+    uint32_t *refs[2];
+    uint32_t *cntv;
+    uint4 *pairs;               // the share's own region of the pair list
+    uint8_t *codes;
+    uint32_t a_base, b_base;    // first scratch slot of region A / B
+};
 
-// offsets of the next round: exclusive scan of ceil(k / 2); also records the largest k of this round.
-// (Three launches, same structure as k_scan_local / k_scan_bsum / k_scan_add.)
-static __global__ void __launch_bounds__(SCAN_T) k_ba_scan_local(BaArgs a) {
-    __shared__ uint32_t sh[SCAN_T];
-    __shared__ uint32_t smax;
-    if (a.round > 0 && a.maxcnt[a.round - 1] <= 1u) return;   // previous round did not run: nothing left
-    if (threadIdx.x == 0) smax = 0;
-    uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
-    uint32_t v[SCAN_E], s = 0, mx = 0;
-    for (int e = 0; e < SCAN_E; ++e) {
-        uint32_t k = (base + e < a.K) ? a.off_cur[base + e + 1] - a.off_cur[base + e] : 0u;
-        mx = max(mx, k);
-        v[e] = (k + 1u) >> 1;
-        s += v[e];
-    }
-    sh[threadIdx.x] = s;
-    __syncthreads();
-    atomicMax(&smax, mx);
-    for (int d = 1; d < SCAN_T; d <<= 1) {
-        uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
-        __syncthreads();
-        sh[threadIdx.x] += t;
-        __syncthreads();
-    }
-    uint32_t excl = sh[threadIdx.x] - s;
-    for (int e = 0; e < SCAN_E; ++e) { if (base + e < a.K) a.off_next[base + e] = excl; excl += v[e]; }
-    if (threadIdx.x == SCAN_T - 1) a.bsum[blockIdx.x] = sh[SCAN_T - 1];
-    if (threadIdx.x == 0) atomicMax(&a.maxcnt[a.round], smax);
-}
-static __global__ void __launch_bounds__(SCAN_T) k_ba_scan_bsum(BaArgs a) {
-    if (!ba_round_active(a)) return;
-    __shared__ uint32_t sh[SCAN_T];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (uint32_t base = 0; base < a.nscan; base += SCAN_T) {
-        uint32_t i = base + threadIdx.x;
-        uint32_t s = (i < a.nscan) ? a.bsum[i] : 0u;
-        sh[threadIdx.x] = s;
-        __syncthreads();
-        for (int d = 1; d < SCAN_T; d <<= 1) {
-            uint32_t t = (threadIdx.x >= (unsigned)d) ? sh[threadIdx.x - d] : 0u;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
-        }
-        if (i < a.nscan) a.bsum[i] = carry + sh[threadIdx.x] - s;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += sh[SCAN_T - 1];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) a.off_next[a.K] = carry;
-}
-static __global__ void __launch_bounds__(SCAN_T) k_ba_scan_add(BaArgs a) {
-    if (!ba_round_active(a)) return;
-    uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_E;
-    uint32_t add = a.bsum[blockIdx.x];
-    for (int e = 0; e < SCAN_E; ++e)
-        if (base + e < a.K) a.off_next[base + e] += add;
+__device__ __forceinline__ const uint32_t *ba_ref_ptr(const BaArgs &a, uint32_t ref, int AFFW) {
+    return ((ref & REF_SCRATCH) ? a.scratch : a.bases) + (size_t)(ref & REF_IDX) * AFFW;
 }
 
-// Plan of a round.  For every output point j: its bucket b (binary search in off_next), local index l, and
-// its inputs off_cur[b] + 2l (+ 1 when the bucket still has a partner for it).  Real additions are appended
-// to the round's pair list (warp-aggregated atomic; order is irrelevant, each pair carries its output
-// index); an input without a partner -- or whose partner is infinity -- is copied to its output slot right
-// here, so that the arithmetic kernel sees additions only.
-//   round 0 : sources are sorted entries (table row | sign << 31), never infinity (filtered by the sort)
-//   later   : sources are indices into the previous round's output, with its infinity flags
-template <class G, bool FIRST>
-__global__ void __launch_bounds__(256) k_ba_plan(BaArgs a) {
-    typedef typename G::F F;
-    typedef typename F::M M;
-    constexpr int DEG = F::DEG, EW = DEG * NLIMB, AFFW = 2 * EW;
-    if (!ba_round_active(a)) return;
-    const uint32_t E = a.off_next[a.K];
-    const uint32_t *in = FIRST ? a.bases : a.in_pts;
-    const int lane = threadIdx.x & 31;
-    const uint32_t stride = gridDim.x * blockDim.x;
-    const uint32_t iters = (E + stride - 1) / stride;
-    for (uint32_t it = 0; it < iters; ++it) {
-        const uint32_t j = it * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = j < E;
-        uint32_t s0 = 0, s1 = BA_NONE;
-        bool s0_inf = false;
-        // the 32 outputs of a warp are consecutive: two full binary searches (its first and last output) bound
-        // the few-step search of every lane in between
-        const uint32_t jw0 = j - (uint32_t)lane;
-        uint32_t bb = 0;
-        if ((lane == 0 || lane == 31) && jw0 < E) bb = bucket_of(a.off_next, a.K, lane == 0 ? jw0 : min(jw0 + 31u, E - 1u));
-        const uint32_t b_first = __shfl_sync(0xffffffffu, bb, 0), b_last = __shfl_sync(0xffffffffu, bb, 31);
+// Start of share t: t * T, moved back to the start of its bucket unless that bucket is a giant (more than half a
+// share), which is cut right there.  Monotone in t; share t is [boundary(t), boundary(t + 1)).
+__device__ __forceinline__ uint32_t ba_boundary(const BaArgs &a, uint32_t t, uint32_t E) {
+    const unsigned long long e = (unsigned long long)t * a.T;
+    if (t >= a.U || e >= E) return E;
+    const uint32_t b = bucket_of(a.offs, a.K, (uint32_t)e);
+    const uint32_t lo = a.offs[b], hi = a.offs[b + 1];
+    return (hi - lo > a.T / 2u) ? (uint32_t)e : lo;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+// Plan of round r for one share (executed by ONE warp): lane per piece.  Every pair of consecutive references of a
+// piece becomes an addition appended to the share's pair list (an infinite operand short-circuits: the other one is
+// passed on, the pair is marked idle), an odd one out is carried over, the piece's count is halved.
+// Returns the number of pairs listed (idle ones included).
+__device__ __forceinline__ uint32_t ba_plan(const BaView &v, uint32_t r, int lane, uint32_t &maxc) {
+#ifdef BA_DBG_VOLATILE_REFS
+    const volatile uint32_t *cur = v.refs[r & 1u];
+#else
+    const uint32_t *cur = v.refs[r & 1u];
+#endif
+    uint32_t *nxt = v.refs[(r + 1u) & 1u];
+    uint32_t total = 0;
+    for (uint32_t base = 0; base < v.npieces; base += 32u) {
+        const uint32_t q = base + (uint32_t)lane;
+        const bool valid = q < v.npieces;
+        const uint32_t b = v.b0 + q;
+        uint32_t ps = 0, c = 0;
         if (valid) {
-            uint32_t blo = b_first, bhi = b_last + 1u;   // invariant: off_next[blo] <= j < off_next[bhi]
-            while (bhi - blo > 1u) {
-                const uint32_t mid = blo + ((bhi - blo) >> 1);
-                if (a.off_next[mid] <= j) blo = mid; else bhi = mid;
-            }
-            const uint32_t b = blo;
-            const uint32_t l = j - a.off_next[b];
-            const uint32_t lo = a.off_cur[b], cnt = a.off_cur[b + 1] - lo;
-            const uint32_t i0 = lo + 2u * l;
-            const bool has2 = 2u * l + 1u < cnt;
-            if (FIRST) {
-                s0 = a.entries[i0];
-                if (has2) s1 = a.entries[i0 + 1];
-            } else {
-                const bool inf0 = a.in_inf[i0] != 0;
-                const bool inf1 = has2 ? a.in_inf[i0 + 1] != 0 : true;
-                if (has2 && !inf0 && !inf1) { s0 = i0; s1 = i0 + 1; }
-                else if (has2 && inf0 && !inf1) s0 = i0 + 1;
-                else { s0 = i0; s0_inf = inf0; }
-            }
+            ps = max(v.offs[b], v.E0);
+            c = (r == 0u) ? min(v.offs[b + 1], v.E1) - ps : v.cntv[b + v.id];
         }
-        const bool is_pair = valid && s1 != BA_NONE;
-        const unsigned m = __ballot_sync(0xffffffffu, is_pair);
-        uint32_t base = 0;
-        if (lane == 0 && m) base = atomicAdd(a.npairs + a.round, (uint32_t)__popc(m));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (is_pair) a.pairs[base + __popc(m & ((1u << lane) - 1u))] = make_uint4(s0, s1, j, 0u);
-        if (valid && !is_pair) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(in + (size_t)(s0 & 0x7fffffffu) * AFFW);
-            uint4 *dst = reinterpret_cast<uint4 *>(a.out_pts + (size_t)j * AFFW);
-#pragma unroll
-            for (int q = 0; q < DEG * QUADS; ++q) dst[q] = src[q];
-            const bool neg = FIRST && (s0 >> 31);
-#pragma unroll
-            for (int c = 0; c < DEG; ++c) {
-                fq_t y, ny;
-#pragma unroll
-                for (int q = 0; q < QUADS; ++q) { uint4 v = src[(DEG + c) * QUADS + q]; y[4 * q] = v.x; y[4 * q + 1] = v.y; y[4 * q + 2] = v.z; y[4 * q + 3] = v.w; }
-                if (neg) { fq_neg<M>(ny, y);
-#pragma unroll
-                    for (int i = 0; i < NLIMB; ++i) y[i] = ny[i]; }
-#pragma unroll
-                for (int q = 0; q < QUADS; ++q) { uint4 v; v.x = y[4 * q]; v.y = y[4 * q + 1]; v.z = y[4 * q + 2]; v.w = y[4 * q + 3]; dst[(DEG + c) * QUADS + q] = v; }
-            }
-            a.out_inf[j] = s0_inf ? 1 : 0;
+        maxc = max(maxc, c);
+        const uint32_t np = c >> 1;
+        const uint32_t incl = warp_incl_scan(np, lane);
+        const uint32_t first = total + incl - np;
+        const uint32_t out0 = (r & 1u) ? v.b_base + ((ps + b + v.id) >> 2) : v.a_base + (ps >> 1);
+        for (uint32_t j = 0; j < np; ++j) {
+            const uint32_t r1 = cur[ps + 2u * j], r2 = cur[ps + 2u * j + 1u];
+            // An infinite operand: the other one is COPIED to the pair's output slot (d.y = REF_INF), not passed on by
+            // reference -- a reference handed through would outlive the round its slot is reserved for (the slot
+            // scheme above recycles a piece's slots every second round) and be overwritten under the reader.
+            uint4 d;
+            if (r1 == REF_INF && r2 == REF_INF) {
+                nxt[ps + j] = REF_INF;
+                d = make_uint4(REF_INF, REF_INF, 0u, 0u);
+            } else if (r1 == REF_INF) d = make_uint4(r2, REF_INF, out0 + j, ps + j);
+            else d = make_uint4(r1, r2, out0 + j, ps + j);
+            v.pairs[first + j] = d;
         }
+        if (c & 1u) nxt[ps + np] = cur[ps + c - 1u];
+        if (valid) v.cntv[b + v.id] = (c + 1u) >> 1;
+        total += __shfl_sync(0xffffffffu, incl, 31);
     }
+    return total;
 }
 
 template <class G>
 struct BaCfg {
     static constexpr int DEG = G::F::DEG;
-    // PREFETCH (experiment, off): three more slots double-buffer the gathers (cp.async straight into the slab
-    // while the previous addition is being computed); 27 KB of slab per warp then allow 8 warps per SM instead
-    // of 12.  Measured on B200 at 2^20: G1 56.3 ms against 54.3 ms without it (Fq2 150.9 vs 146.4) -- with the
-    // sources already pulled into L2 one step ahead (prefetch_coord) the gathers are not what the warps wait
-    // for, and the extra commit/wait traffic costs more than it hides.  8 warps per SM without PREFETCH
-    // (-DB200_BA_MINB=2) is within noise of 12 for G1 / Fq2 and 14 % slower for Fq3.
-#ifndef B200_BA_PREFETCH
-#define B200_BA_PREFETCH 0
-#endif
-    static constexpr bool PREFETCH = B200_BA_PREFETCH && DEG < 3;
-    static constexpr int NSLOT = PREFETCH ? 9 : 6;
-    // ONEBLOCK (default): the twelve warps of an SM form ONE block of 384 threads instead of three blocks of four
-    // warps (four of three for Fq3).  Same occupancy, same code -- but the multiplier measures 7.5-7.7 G modmul/s
-    // with twelve warps in one block against 6.65 as 3 x 128, 4 x 96, 6 x 64 or 12 x 32 threads
-    // (tools/mul_sched_probe.cu, profiles/r01_mul_sched_probe.txt), and the accumulation follows: 2^20 G1
-    // 47.2 -> 43.9 ms, MNT6753 G2 2^18 83.2 -> 69.4 ms.
-#ifndef B200_BA_ONEBLOCK
-#define B200_BA_ONEBLOCK 1
-#endif
-#if B200_BA_ONEBLOCK
+    static constexpr int NSLOT = 6;
+    // The twelve warps of an SM form ONE block of 384 threads (not three blocks of four warps): same occupancy,
+    // same code, but the multiplier measures 7.5-7.7 G modmul/s with twelve warps in one block against 6.65 as
+    // 3 x 128, 4 x 96, 6 x 64 or 12 x 32 threads (tools/mul_sched_probe.cu, profiles/r01_mul_sched_probe.txt).
     static constexpr int TPB = 12 / DEG;
     static constexpr int MINB = 1;
-#else
-    static constexpr int TPB = DEG == 1 ? 4 : (DEG == 2 ? 2 : 1);
-#ifdef B200_BA_MINB
-    static constexpr int MINB = B200_BA_MINB;
-#else
-    static constexpr int MINB = PREFETCH ? 2 : (DEG == 1 ? 3 : (DEG == 2 ? 3 : 4));
-#endif
-#endif
     typedef TeamSetup<G, NSLOT, TPB> TS;
 };
 
@@ -350,176 +282,264 @@ __device__ __forceinline__ void prefetch_coord(const Team<F> &T, const uint32_t 
 #define BA_G2S_WAIT()
 #endif
 
-template <class G, bool FIRST>
+// The additions [p0, p0 + 32 B) of the share's pair list: forward pass, one inversion, backward pass.
+template <class F>
+__device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const BaView &v, uint32_t *nxt_refs, uint32_t p0, uint32_t B,
+                                        uint32_t P) {
+    constexpr int DEG = F::DEG;
+    constexpr int EW = DEG * NLIMB, AFFW = 2 * EW;
+    const int lane = threadIdx.x & 31;
+    const BaSlots s = {0, 1, 2, 3, 4, 5};
+    const uint4 idle = make_uint4(REF_INF, REF_INF, 0u, 0u);
+    // ---- forward: denominators and prefix products
+    T.set_one(s.INV);
+    // descriptors are read two steps ahead and the coordinates of the next step are pulled into L2, so
+    // that neither the list nor the gathers are waited for at DRAM latency
+    uint4 nxt = (p0 + lane < P) ? v.pairs[p0 + lane] : idle;
+    uint4 nxt2 = (B > 1u && p0 + 32u + lane < P) ? v.pairs[p0 + 32u + lane] : idle;
+    for (uint32_t i = 0; i < B; ++i) {
+        const uint32_t p = p0 + i * 32u + lane;
+        const uint4 d = nxt;
+        const bool valid = d.x != REF_INF, has2 = d.y != REF_INF;      // !has2: copy of operand 1
+        const uint32_t *g1 = ba_ref_ptr(a, d.x, AFFW), *g2 = ba_ref_ptr(a, d.y, AFFW);
+        nxt = nxt2;
+        if (nxt.x != REF_INF) {
+            prefetch_coord(T, ba_ref_ptr(a, nxt.x, AFFW));
+            if (nxt.y != REF_INF) prefetch_coord(T, ba_ref_ptr(a, nxt.y, AFFW));
+        }
+        nxt2 = (i + 2 < B && p + 64u < P) ? v.pairs[p + 64u] : idle;
+        BA_G2S_BEGIN();
+        BA_G2S(T, s.X1, g1, valid);
+        BA_G2S(T, s.X2, g2, has2);
+        BA_G2S_WAIT();
+        const uint32_t code = pair_forward(T, s, valid, has2, [&](bool pred) {
+            BA_G2S_BEGIN();
+            BA_G2S(T, s.Y1, g1 + EW, pred);
+            BA_G2S(T, s.Y2, g2 + EW, pred);
+            BA_G2S_WAIT();
+            T.neg_if(s.Y1, s.Y1, (d.x & REF_NEG) != 0u, pred);
+            T.neg_if(s.Y2, s.Y2, (d.y & REF_NEG) != 0u, pred);
+        });
+        if (valid && T.comp == 0) v.codes[p] = (uint8_t)code;                      // parked until the backward pass
+        BA_S2G(T, a.scratch + (size_t)d.z * AFFW, s.INV, valid);                    // exclusive prefix, parked in the output slot
+        T.mul(s.INV, s.INV, s.X2);
+    }
+    // ---- one inversion for the whole tile
+    tile_inverse(T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
+#ifdef BA_DBG_FENCE_TILE
+    __threadfence();
+    T.sync();
+#endif
+    // ---- backward: the additions
+    {
+        const uint32_t pl = p0 + (B - 1u) * 32u + lane;
+        nxt = (pl < P) ? v.pairs[pl] : idle;
+        nxt2 = (B > 1u && pl - 32u < P) ? v.pairs[pl - 32u] : idle;
+    }
+    for (int i = (int)B - 1; i >= 0; --i) {
+        const uint32_t p = p0 + (uint32_t)i * 32u + lane;
+        const uint4 d = nxt;
+        const bool valid = d.x != REF_INF, has2 = d.y != REF_INF;
+        const uint32_t *g1 = ba_ref_ptr(a, d.x, AFFW), *g2 = ba_ref_ptr(a, d.y, AFFW);
+        uint32_t *out = a.scratch + (size_t)d.z * AFFW;
+        nxt = nxt2;
+        if (nxt.x != REF_INF) {
+            const uint32_t *n1 = ba_ref_ptr(a, nxt.x, AFFW), *n2 = ba_ref_ptr(a, nxt.y, AFFW);
+            prefetch_coord(T, n1); prefetch_coord(T, n1 + EW);
+            if (nxt.y != REF_INF) { prefetch_coord(T, n2); prefetch_coord(T, n2 + EW); }
+            prefetch_coord(T, a.scratch + (size_t)nxt.z * AFFW);
+        }
+        nxt2 = (i > 1 && p - 64u < P) ? v.pairs[p - 64u] : idle;
+        const uint32_t code = valid ? v.codes[p] : (uint32_t)BA_IDLE;
+        BA_G2S_BEGIN();
+        BA_G2S(T, s.X1, g1, valid);
+        BA_G2S(T, s.Y1, g1 + EW, valid);
+        BA_G2S(T, s.X2, g2, has2);
+        BA_G2S(T, s.Y2, g2 + EW, has2);
+        BA_G2S(T, s.PRE, out, valid);
+        BA_G2S_WAIT();
+        T.neg_if(s.Y1, s.Y1, (d.x & REF_NEG) != 0u, valid);
+        T.neg_if(s.Y2, s.Y2, (d.y & REF_NEG) != 0u, has2);
+        const bool res_inf = pair_backward(T, s, code);
+        BA_S2G(T, out, s.X2, valid);
+        BA_S2G(T, out + EW, s.Y2, valid);
+        if (valid && T.comp == 0) nxt_refs[d.w] = res_inf ? REF_INF : (REF_SCRATCH | d.z);
+    }
+}
+
+// All rounds of one share.  Returns the number of rounds executed; the survivors are in v.refs[rounds & 1].
+template <class F>
+__device__ __forceinline__ uint32_t ba_share(const Team<F> &T, const BaArgs &a, const BaView &v, uint32_t *s_pairs /* team-shared word */) {
+    const int lane = threadIdx.x & 31;
+    uint32_t r = 0, adds = 0;
+    for (;; ++r) {
+        __threadfence();      // the sums and references of the previous round, written by the team's other lanes and warps
+        T.sync();
+        if (T.comp == 0) {
+            uint32_t maxc = 0;
+            const uint32_t P = ba_plan(v, r, lane, maxc);
+            if (lane == 0) *s_pairs = P;
+            if (r == 0) {
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) maxc = max(maxc, __shfl_xor_sync(0xffffffffu, maxc, d));
+                if (lane == 0) atomicMax(a.ctl + 1, maxc);
+            }
+            if (lane == 0 && P && r < (uint32_t)(BA_CTL_WORDS - 4)) atomicAdd(a.ctl + 4 + r, P);
+        }
+        __threadfence();
+        T.sync();
+        const uint32_t P = *s_pairs;
+        if (P == 0u) break;
+        adds += P;
+        // tiles of at most BA_BMAX additions per lane, the last two of a long list evened out
+        uint32_t p0 = 0;
+        while (p0 < P) {
+            const uint32_t left = (P - p0 + 31u) / 32u;
+            uint32_t B = left;
+            if (left > (uint32_t)BA_BMAX) B = left >= 2u * (uint32_t)BA_BMAX ? (uint32_t)BA_BMAX : (left + 1u) / 2u;
+            ba_tile(T, a, v, v.refs[(r + 1u) & 1u], p0, B, P);
+            p0 += 32u * B;
+        }
+    }
+    if (T.comp == 0 && lane == 0) {
+        atomicMax(a.ctl, r);
+        if (adds) atomicAdd(a.ctl + 2, adds);
+    }
+    return r;
+}
+
+template <class G>
 __global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_batch_add(BaArgs a) {
     typedef typename G::F F;
     typedef BaCfg<G> C;
-    constexpr int DEG = F::DEG;
-    constexpr int EW = DEG * NLIMB, AFFW = 2 * EW;
-    if (!ba_round_active(a)) return;
     extern __shared__ uint4 smem[];
     __shared__ uint32_t s_flags[C::TPB][4];
-    __shared__ uint32_t s_tile[C::TPB];
+    __shared__ uint32_t s_w[C::TPB][4];
     int team;
     const Team<F> T = C::TS::make(smem, s_flags, team);
     const int lane = threadIdx.x & 31;
-    BaSlots s = {0, 1, 2, 3, 4, 5};
-    int NX1 = 6, NX2 = 7, NPRE = 8;   // spare slots of the double buffer (PREFETCH only)
-    const uint32_t *in = FIRST ? a.bases : a.in_pts;
-
-    if (blockIdx.x == 0 && threadIdx.x == 0) *a.nrounds = a.round + 1;
-    const uint32_t E = a.npairs[a.round];
-    // Tile = 32 lanes x B consecutive pairs of the list, claimed from an atomic cursor.  Small rounds: one
-    // tile per team (a round then costs one inversion latency, not several).  Large rounds: full tiles of
-    // BA_BMAX while more than one full tile per team is left, then the remainder in equal shares, so that
-    // the teams finish together without paying for many small tiles (each tile costs one inversion).
-    const uint32_t teams = gridDim.x * C::TPB;
-    const uint32_t B0 = (E + teams * 32u - 1u) / (teams * 32u);
-    const uint4 idle = make_uint4(0u, 0u, 0u, 0u);
-    __shared__ uint32_t s_B[C::TPB];
-
-    bool first_tile = true;
-    for (;;) {
+    const uint32_t E = a.offs[a.K];
+    a.T = max(1u, (E + a.U - 1u) / a.U);
+    // shares are dealt round-robin over the blocks so that a short list still spreads over all SMs
+    for (uint32_t t = (uint32_t)team * gridDim.x + blockIdx.x; t < a.U; t += gridDim.x * C::TPB) {
         T.sync();
         if (T.comp == 0 && lane == 0) {
-            uint32_t Bt;
-            if (B0 <= (uint32_t)BA_BMAX) Bt = B0 < 1u ? 1u : B0;
-            else {
-                const uint32_t cur = *reinterpret_cast<volatile uint32_t *>(a.tile_counter + a.round);
-                const uint32_t rem = E > cur ? E - cur : 0u;
-                Bt = (rem + teams * 32u - 1u) / (teams * 32u);
-                Bt = Bt < 16u ? 16u : (Bt > (uint32_t)BA_BMAX ? (uint32_t)BA_BMAX : Bt);
-#ifdef B200_BA_STAGGER
-                // (experiment, off: measured 48.3 vs 47.3 ms) all teams start a round together; first tiles of
-                // different lengths keep their forward / inversion / backward phases from lining up across the SM
-                if (first_tile) Bt = max(16u, Bt * (((blockIdx.x + (uint32_t)team) & 3u) + 1u) / 4u);
-#endif
-            }
-            s_tile[team] = atomicAdd(a.tile_counter + a.round, 32u * Bt);
-            s_B[team] = Bt;
+            const uint32_t E0 = ba_boundary(a, t, E), E1 = ba_boundary(a, t + 1u, E);
+            s_w[team][0] = E0;
+            s_w[team][1] = E1;
+            s_w[team][2] = E0 < E1 ? bucket_of(a.offs, a.K, E0) : 0u;
+            s_w[team][3] = E0 < E1 ? bucket_of(a.offs, a.K, E1 - 1u) : 0u;
         }
         T.sync();
-        const uint32_t base = s_tile[team];
-        const uint32_t B = s_B[team];
-        first_tile = false;
-        if (base >= E) break;
+        BaView v;
+        v.offs = a.offs;
+        v.E0 = s_w[team][0];
+        v.E1 = s_w[team][1];
+        v.b0 = s_w[team][2];
+        const uint32_t b1 = s_w[team][3];
+        T.sync();
+        if (v.E0 >= v.E1) continue;
+        v.npieces = b1 - v.b0 + 1u;
+        v.id = t;
+        v.refs[0] = a.refs[0];
+        v.refs[1] = a.refs[1];
+        v.cntv = a.cntv;
+        v.pairs = a.pairs + (v.E0 >> 1) + t;
+        v.codes = a.codes + (v.E0 >> 1) + t;
+        v.a_base = 0u;
+        v.b_base = a.capA;
+        const uint32_t rounds = ba_share(T, a, v, &s_w[team][0]);
+        // what is left of every piece: whole buckets are final, cut ones go to the boundary list
+        if (T.comp == 0) {
+            const uint32_t *cur = a.refs[rounds & 1u];
+            for (uint32_t q = (uint32_t)lane; q < v.npieces; q += 32u) {
+                const uint32_t b = v.b0 + q;
+                const uint32_t lo = a.offs[b], hi = a.offs[b + 1];
+                const uint32_t ps = max(lo, v.E0), pe = min(hi, v.E1);
+                const uint32_t c = rounds ? a.cntv[b + t] : pe - ps;
+                const uint32_t ref = c ? cur[ps] : REF_INF;
+                if (lo >= v.E0 && hi <= v.E1) a.bucket_ref[b] = ref;
+                else {
+                    const uint32_t slot = 2u * t + (lo < v.E0 ? 0u : 1u);
+                    a.bnd_ref[slot] = ref;
+                    a.bnd_bucket[slot] = b;
+                }
+            }
+        }
+    }
+}
 
-        // ---- forward: denominators and prefix products
-        T.set_one(s.INV);
-        // descriptors are read two steps ahead and the coordinates of the next step are pulled into L2, so
-        // that neither the list nor the gathers are waited for at DRAM latency
-        uint4 nxt = (base + lane < E) ? a.pairs[base + lane] : idle;
-        uint4 nxt2 = (B > 1u && base + 32u + lane < E) ? a.pairs[base + 32u + lane] : idle;
-        for (uint32_t i = 0; i < B; ++i) {
-            const uint32_t p = base + i * 32u + lane;
-            const bool valid = p < E;
-            const uint4 d = nxt;
-            const uint32_t r1 = d.x & 0x7fffffffu, r2 = d.y & 0x7fffffffu, j = d.z;
-            nxt = nxt2;
-            if (i + 1 < B && p + 32u < E) {
-                prefetch_coord(T, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW);
-                prefetch_coord(T, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW);
+// Pieces of split buckets (k_batch_add's boundary list) -> one reference per split bucket.  One team: the pieces are
+// compacted into a list of their own, runs of equal bucket id are its buckets, and the same rounds reduce it.
+// With no giant bucket in the MSM the list is empty and the kernel returns at once.
+template <class G>
+__global__ void __launch_bounds__(BaCfg<G>::TS::THREADS, BaCfg<G>::MINB) k_ba_fixup(BaArgs a) {
+    typedef typename G::F F;
+    typedef BaCfg<G> C;
+    extern __shared__ uint4 smem[];
+    __shared__ uint32_t s_flags[C::TPB][4];
+    __shared__ uint32_t s_w[4];
+    int team;
+    const Team<F> T = C::TS::make(smem, s_flags, team);
+    if (team != 0) return;
+    const int lane = threadIdx.x & 31;
+    if (T.comp == 0) {
+        // compaction of the occupied slots (slot order = list order, so pieces of one bucket are consecutive)
+        uint32_t n = 0, nb = 0, prev = REF_INF;
+        for (uint32_t base = 0; base < 2u * a.U; base += 32u) {
+            const uint32_t i = base + (uint32_t)lane;
+            const uint32_t bk = i < 2u * a.U ? a.bnd_bucket[i] : REF_INF;
+            const bool occ = bk != REF_INF;
+            const unsigned m = __ballot_sync(0xffffffffu, occ);
+            const uint32_t pos = n + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            // bucket id of the previous occupied slot: the nearest lower occupied lane, else the carry
+            uint32_t before = prev;
+            {
+                const unsigned lower = m & ((1u << lane) - 1u);
+                const int src = lower ? 31 - __clz((int)lower) : 0;
+                const uint32_t vsrc = __shfl_sync(0xffffffffu, bk, src);
+                if (lower) before = vsrc;
             }
-            nxt2 = (i + 2 < B && p + 64u < E) ? a.pairs[p + 64u] : idle;
-            if (C::PREFETCH) {
-                if (i == 0) {
-                    g2s_async(T, s.X1, in + (size_t)r1 * AFFW, valid);
-                    g2s_async(T, s.X2, in + (size_t)r2 * AFFW, valid);
-                    async_commit();
-                }
-                const bool more = i + 1 < B;
-                if (more) {      // next step's abscissae land in the spare slots while this step computes
-                    const bool nv = p + 32u < E;
-                    g2s_async(T, NX1, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, nv);
-                    g2s_async(T, NX2, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW, nv);
-                    async_commit();
-                    async_wait<1>();
-                } else async_wait<0>();
-            } else {
-                BA_G2S_BEGIN();
-                BA_G2S(T, s.X1, in + (size_t)r1 * AFFW, valid);
-                BA_G2S(T, s.X2, in + (size_t)r2 * AFFW, valid);
-                BA_G2S_WAIT();
+            const bool head = occ && bk != before;
+            const unsigned hm = __ballot_sync(0xffffffffu, head);
+            if (occ) a.fx_refs[0][pos] = a.bnd_ref[i];
+            if (head) {
+                const uint32_t hpos = nb + (uint32_t)__popc(hm & ((1u << lane) - 1u));
+                a.fx_offs[hpos] = pos;
+                a.fx_bucket[hpos] = bk;
             }
-            const uint32_t code = pair_forward(T, s, valid, valid, [&](bool pred) {
-                BA_G2S_BEGIN();
-                BA_G2S(T, s.Y1, in + (size_t)r1 * AFFW + EW, pred);
-                BA_G2S(T, s.Y2, in + (size_t)r2 * AFFW + EW, pred);
-                BA_G2S_WAIT();
-                if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, pred); T.neg_if(s.Y2, s.Y2, d.y >> 31, pred); }
-            });
-            if (valid && T.comp == 0) a.out_inf[j] = (uint8_t)code;   // parked until the backward pass
-            BA_S2G(T, a.out_pts + (size_t)j * AFFW, s.INV, valid);       // exclusive prefix, parked in the output slot
-            T.mul(s.INV, s.INV, s.X2);
-            if (C::PREFETCH) { int t = s.X1; s.X1 = NX1; NX1 = t; t = s.X2; s.X2 = NX2; NX2 = t; }
+            if (m) prev = __shfl_sync(0xffffffffu, bk, 31 - __clz((int)m));
+            n += (uint32_t)__popc(m);
+            nb += (uint32_t)__popc(hm);
         }
-        // ---- one inversion for the whole tile
-        tile_inverse(T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
-        // ---- backward: the additions
-        {
-            const uint32_t pl = base + (B - 1u) * 32u + lane;
-            nxt = (pl < E) ? a.pairs[pl] : idle;
-            nxt2 = (B > 1u && pl - 32u < E) ? a.pairs[pl - 32u] : idle;
-        }
-        for (int i = (int)B - 1; i >= 0; --i) {
-            const uint32_t p = base + (uint32_t)i * 32u + lane;
-            const bool valid = p < E;
-            const uint4 d = nxt;
-            const uint32_t r1 = d.x & 0x7fffffffu, r2 = d.y & 0x7fffffffu, j = d.z;
-            nxt = nxt2;
-            if (i > 0 && p - 32u < E) {
-                const uint32_t *n1 = in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, *n2 = in + (size_t)(nxt.y & 0x7fffffffu) * AFFW;
-                prefetch_coord(T, n1); prefetch_coord(T, n1 + EW);
-                prefetch_coord(T, n2); prefetch_coord(T, n2 + EW);
-                prefetch_coord(T, a.out_pts + (size_t)nxt.z * AFFW);
-                prefetch_l2(a.out_inf + nxt.z);
-            }
-            nxt2 = (i > 1 && p - 64u < E) ? a.pairs[p - 64u] : idle;
-            const uint32_t code = valid ? a.out_inf[j] : (uint32_t)BA_IDLE;
-            bool res_inf;
-            if (C::PREFETCH) {
-                if (i == (int)B - 1) {   // first step of the pass: nothing was prefetched for it
-                    g2s_async(T, s.X1, in + (size_t)r1 * AFFW, valid);
-                    g2s_async(T, s.X2, in + (size_t)r2 * AFFW, valid);
-                    g2s_async(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
-                    async_commit();
-                }
-                g2s_async(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);      // needed after two products
-                g2s_async(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
-                async_commit();
-                const bool more = i > 0;
-                if (more) {              // next step: abscissae and prefix into the spare slots
-                    const bool nv = p - 32u < E;
-                    g2s_async(T, NX1, in + (size_t)(nxt.x & 0x7fffffffu) * AFFW, nv);
-                    g2s_async(T, NX2, in + (size_t)(nxt.y & 0x7fffffffu) * AFFW, nv);
-                    g2s_async(T, NPRE, a.out_pts + (size_t)nxt.z * AFFW, nv);
-                    async_commit();
-                    async_wait<2>();
-                } else async_wait<1>();
-                if (team_any(code == BA_DBL)) { if (more) async_wait<1>(); else async_wait<0>(); }
-                if (FIRST && team_any(code == BA_DBL)) T.neg_if(s.Y1, s.Y1, d.x >> 31, valid);
-                pair_backward_head(T, s, code);
-                if (more) async_wait<1>(); else async_wait<0>();
-                if (FIRST) {
-                    if (!team_any(code == BA_DBL)) T.neg_if(s.Y1, s.Y1, d.x >> 31, valid);
-                    T.neg_if(s.Y2, s.Y2, d.y >> 31, valid);
-                }
-                res_inf = pair_backward_tail(T, s, code);
-            } else {
-                BA_G2S_BEGIN();
-                BA_G2S(T, s.X1, in + (size_t)r1 * AFFW, valid);
-                BA_G2S(T, s.Y1, in + (size_t)r1 * AFFW + EW, valid);
-                BA_G2S(T, s.X2, in + (size_t)r2 * AFFW, valid);
-                BA_G2S(T, s.Y2, in + (size_t)r2 * AFFW + EW, valid);
-                BA_G2S(T, s.PRE, a.out_pts + (size_t)j * AFFW, valid);
-                BA_G2S_WAIT();
-                if (FIRST) { T.neg_if(s.Y1, s.Y1, d.x >> 31, valid); T.neg_if(s.Y2, s.Y2, d.y >> 31, valid); }
-                res_inf = pair_backward(T, s, code);
-            }
-            BA_S2G(T, a.out_pts + (size_t)j * AFFW, s.X2, valid);
-            BA_S2G(T, a.out_pts + (size_t)j * AFFW + EW, s.Y2, valid);
-            if (valid && T.comp == 0) a.out_inf[j] = res_inf ? 1 : 0;
-            if (C::PREFETCH) { int t = s.X1; s.X1 = NX1; NX1 = t; t = s.X2; s.X2 = NX2; NX2 = t; t = s.PRE; s.PRE = NPRE; NPRE = t; }
+        if (lane == 0) { a.fx_offs[nb] = n; s_w[0] = n; s_w[1] = nb; }
+    }
+    __threadfence_block();
+    T.sync();
+    const uint32_t n = s_w[0], nb = s_w[1];
+    if (n == 0u) return;
+    BaView v;
+    v.offs = a.fx_offs;
+    v.E0 = 0u;
+    v.E1 = n;
+    v.b0 = 0u;
+    v.npieces = nb;
+    v.id = 0u;
+    v.refs[0] = a.fx_refs[0];
+    v.refs[1] = a.fx_refs[1];
+    v.cntv = a.fx_cntv;
+    v.pairs = a.pairs;          // k_batch_add is over: its pair list is free
+    v.codes = a.codes;
+    v.a_base = a.fx_scratch_base;
+    v.b_base = a.fx_scratch_base + a.U + 1u;
+    T.sync();
+    const uint32_t rounds = ba_share(T, a, v, &s_w[2]);
+    if (T.comp == 0) {
+        const uint32_t *cur = a.fx_refs[rounds & 1u];
+        for (uint32_t q = (uint32_t)lane; q < nb; q += 32u) {
+            const uint32_t ps = a.fx_offs[q];
+            const uint32_t c = rounds ? a.fx_cntv[q] : a.fx_offs[q + 1] - ps;
+            a.bucket_ref[a.fx_bucket[q]] = c ? cur[ps] : REF_INF;
         }
     }
 }

@@ -127,11 +127,7 @@ struct Team {
                 if (j < 0) j += DEG;
                 src.p[i] = elem(b, j);
             }
-#if defined(MNT753_MUL_ROLL) && MNT753_MUL_ROLL > 0
-            fq_dot_rolled<M, DEG, MNT753_MUL_ROLL>(res[MSM_CI(c)], aa, src);
-#else
             fq_dot<M, DEG>(res[MSM_CI(c)], aa, src);
-#endif
         }
         sync();
         MSM_FOR_COMP(c) st(d, c, res[MSM_CI(c)], pred);

@@ -3,17 +3,26 @@
 // builds in parallel; msm.cu reaches them through the GroupOps table.
 #pragma once
 #include "host_ctx.cuh"
-#include "batch_affine.cuh"
 
 namespace {
 
+// teams that take a share of an MSM with at most `emax` sorted entries: every team of the persistent grid, but no
+// share below 256 entries (eight additions per lane: below that a round is all fixed cost)
+template <class G>
+uint32_t shares_for(const b200msm_ctx *ctx, uint64_t emax) {
+    const uint64_t teams = (uint64_t)ctx->sm_count * BaCfg<G>::TPB;
+    if (const char *e = getenv("B200MSM_SHARES")) return (uint32_t)std::max(1, atoi(e));   // development knob
+    return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(teams, emax / 256));
+}
+
 template <class G>
 Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) {
-    typedef AccCfg<G> AC;
-    constexpr size_t JACB = 3 * G::F::DEG * NLIMB * 4;
+    constexpr size_t JACB = 3 * G::F::DEG * NLIMB * 4, AFFB = 2 * G::F::DEG * NLIMB * 4;
     Plan p;
     MsmArgs &a = p.a;
+    BaArgs &b = p.b;
     memset(&a, 0, sizeof a);
+    memset(&b, 0, sizeof b);
     const int c = cfg.c;
     a.n = (uint32_t)n;
     a.c = c;
@@ -22,13 +31,6 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     a.NB = 1u << (c - 1);
     a.K = (uint32_t)a.W * a.NB;
     const uint64_t emax = (uint64_t)n * a.Wd;
-    // lanes resident on the device in k_accumulate; aim at ~6 chunks per lane for load balance
-    const uint64_t lanes = (uint64_t)ctx->sm_count * AC::MINB * AC::TPB * 32;
-    uint64_t L = emax / (lanes * 6);
-    if (L < 8) L = 8;
-    if (L > 256) L = 256;
-    a.L = (uint32_t)L;
-    a.max_chunks = (uint32_t)((emax + L - 1) / L) + 1;
     // bucket-reduce segment length: keep >= ~32k lanes of segments when there are that many buckets
     // (one wave of k_bucket_reduce: its 12-slot teams fit 6 per SM for G1, fewer for the towers)
     typedef TailCfg<G> TCp;
@@ -46,38 +48,33 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     a.offs = (uint32_t *)take(((size_t)a.K + 1) * 4);
     a.cursor = (uint32_t *)take((size_t)a.K * 4);
     p.bsum = (uint32_t *)take((size_t)p.nscan * 4);
-    a.group_counter = (uint32_t *)take(4);
     a.entries = (uint32_t *)take((size_t)emax * 4 + 4);
-    if (ctx->accumulator == 0) {
-        // batched-affine rounds: a round halves every bucket (rounding up), so its output has at most
-        // (S + min(K, S)) / 2 points for an input of S
-        constexpr size_t AFFB = 2 * G::F::DEG * NLIMB * 4;
-        uint64_t s1 = (emax + std::min<uint64_t>(a.K, emax) + 1) / 2, s2 = (s1 + std::min<uint64_t>(a.K, s1) + 1) / 2;
-        p.ba_cap[0] = s1 + 1;
-        p.ba_cap[1] = s2 + 1;
-        // occupancy of a bucket is at most n * (digits per bucket set)
-        const uint64_t occ = (uint64_t)n * ((a.Wd + a.W - 1) / a.W);
-        p.ba_rounds = 1;
-        while ((1ull << p.ba_rounds) < occ) ++p.ba_rounds;
-        for (int i = 0; i < 2; ++i) {
-            a.ba_pts[i] = (uint32_t *)take(p.ba_cap[i] * AFFB);
-            a.ba_inf[i] = (uint8_t *)take(p.ba_cap[i]);
-        }
-        a.ba_off[0] = a.offs;
-        a.ba_off[1] = (uint32_t *)take(((size_t)a.K + 1) * 4);
-        p.ba_pairs = (uint4 *)take((emax / 2 + 1) * 16);
-        p.ba_ctl = (uint32_t *)take((size_t)(3 * p.ba_rounds + 4) * 4);   // nrounds | maxcnt[R + 1] | tile_counter[R] | npairs[R]
-        a.ba_nrounds = p.ba_ctl;
-    } else {
-        a.buckets = (uint32_t *)take((size_t)a.K * JACB);
-        a.edges = (uint32_t *)take((size_t)a.max_chunks * 2 * JACB);
-        a.edge_bucket = (uint32_t *)take((size_t)a.max_chunks * 2 * 4);
-        const size_t n1 = (a.max_chunks + FOLD_GS - 1) / FOLD_GS, n2 = (n1 + FOLD_GS - 1) / FOLD_GS;
-        a.fold_pts[0] = (uint32_t *)take(n1 * 2 * JACB);
-        a.fold_key[0] = (uint32_t *)take(n1 * 2 * 4);
-        a.fold_pts[1] = (uint32_t *)take(n2 * 2 * JACB);
-        a.fold_key[1] = (uint32_t *)take(n2 * 2 * 4);
-    }
+    // batched-affine accumulation: reference lists, sums of even rounds (region A: a piece starting at list entry
+    // e puts sum j at (e >> 1) + j), of odd rounds (region B: ((e + bucket + share) >> 2) + j), the fix-up's own
+    // small regions, pair list and codes (share t starts at (E0 >> 1) + t)
+    const uint32_t U = shares_for<G>(ctx, emax);
+    const uint64_t capA = emax / 2 + 1, capB = (emax + a.K + U) / 4 + 2, capF = 2 * (uint64_t)U + 2;
+    b.K = a.K;
+    b.U = U;
+    b.offs = a.offs;
+    b.refs[0] = a.entries;
+    b.refs[1] = (uint32_t *)take((size_t)emax * 4 + 4);
+    b.scratch = (uint32_t *)take((size_t)(capA + capB + capF) * AFFB);
+    b.capA = (uint32_t)capA;
+    b.fx_scratch_base = (uint32_t)(capA + capB);
+    b.pairs = (uint4 *)take((size_t)(emax / 2 + U + 1) * 16);
+    b.codes = (uint8_t *)take((size_t)(emax / 2 + U + 1));
+    b.cntv = (uint32_t *)take(((size_t)a.K + U) * 4);
+    b.bucket_ref = (uint32_t *)take((size_t)a.K * 4);
+    b.bnd_ref = (uint32_t *)take((size_t)2 * U * 4);
+    b.bnd_bucket = (uint32_t *)take((size_t)2 * U * 4);
+    b.ctl = (uint32_t *)take((size_t)BA_CTL_WORDS * 4);
+    for (int i = 0; i < 2; ++i) b.fx_refs[i] = (uint32_t *)take((size_t)2 * U * 4);
+    b.fx_offs = (uint32_t *)take(((size_t)2 * U + 1) * 4);
+    b.fx_cntv = (uint32_t *)take(((size_t)2 * U + 1) * 4);
+    b.fx_bucket = (uint32_t *)take((size_t)2 * U * 4);
+    a.bucket_ref = b.bucket_ref;
+    a.ba_scratch = b.scratch;
     a.segsum = (uint32_t *)take((size_t)a.W * a.nseg * JACB);
     const size_t lvl = (size_t)a.W * ((a.nseg + 31) / 32) * JACB;
     a.tmp_a = (uint32_t *)take(lvl);
@@ -94,6 +91,27 @@ int set_smem(b200msm_ctx *ctx, K kernel, size_t bytes) {
     return B200MSM_OK;
 }
 
+// shared-memory attributes of every kernel of the group, once per context (they are per device)
+template <class G>
+int prepare_kernels(b200msm_ctx *ctx) {
+    typedef TailCfg<G> TC;
+    bool &done = ctx->kernels_ready[G::GROUP];
+    if (done) return B200MSM_OK;
+    int rc;
+    if ((rc = set_smem(ctx, k_batch_add<G>, BaCfg<G>::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_ba_fixup<G>, BaCfg<G>::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_bucket_reduce<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_sum<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_horner<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_to_affine<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_scalar_mul<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_synth_bases<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_batch_normalise<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_dbl_many<G>, DblCfg<G>::TS::SMEM))) return rc;
+    done = true;
+    return B200MSM_OK;
+}
+
 int grow_arena(b200msm_ctx *ctx, Lane &ln, size_t bytes) {
     if (bytes <= ln.arena_bytes) return B200MSM_OK;
     CU(cudaStreamSynchronize(ln.stream));
@@ -106,16 +124,20 @@ int grow_arena(b200msm_ctx *ctx, Lane &ln, size_t bytes) {
     return B200MSM_OK;
 }
 
+template <class G>
+TabCfg cfg_for(const b200msm_ctx *ctx, const BaseSet &bs, size_t n) {
+    // window tables are used when they exist and the caller did not force a different window width
+    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) return TabCfg{bs.c_tab, digits_for(bs.c_tab), bs.NT, bs.G};
+    return choose_cfg(n, G::F::DEG, ctx->c_override, 0, false);
+}
+
 // Size lane `li`'s arena for MSMs of n points over `bs` and set the kernels' shared-memory attributes now, so
 // that the first MSM does not pay for them (b200msm_key_load warms every lane it is going to use).
 template <class G>
 int reserve_lane(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t n) {
-    constexpr int DEG = G::F::DEG;
-    if (n == 0) return B200MSM_OK;
-    TabCfg cfg;
-    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) cfg = {bs.c_tab, digits_for(bs.c_tab), bs.NT, bs.G};
-    else cfg = choose_cfg(n, DEG, ctx->c_override, 0, false);
-    Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
+    int rc = prepare_kernels<G>(ctx);
+    if (rc || n == 0) return rc;
+    Plan probe = make_plan<G>(ctx, n, cfg_for<G>(ctx, bs, n), nullptr);
     return grow_arena(ctx, ctx->lanes[li], probe.bytes);
 }
 
@@ -124,14 +146,15 @@ template <class G>
 int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, const uint64_t *scalars, size_t n,
                 uint64_t *out_xyz) {
     typedef typename G::F F;
-    typedef AccCfg<G> AC;
     typedef TailCfg<G> TC;
+    typedef BaCfg<G> BC;
     constexpr int DEG = F::DEG;
     constexpr size_t AFFW = 2 * DEG * NLIMB, JACW = 3 * DEG * NLIMB;
     Lane &ln = ctx->lanes[li];
     cudaStream_t st = ln.stream;
     ln.out_words = JACW / 2;
     ln.user_out = out_xyz;
+    ln.ctl_valid = false;
 
     if (n == 0) {
         // empty sum: infinity, reported as (1, 1, 0) in Montgomery form like curves.cu:104-114
@@ -147,31 +170,22 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
         return B200MSM_OK;
     }
 
-    // window tables are used when they exist and the caller did not force a different window width
-    TabCfg cfg;
-    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) cfg = {bs.c_tab, digits_for(bs.c_tab), bs.NT, bs.G};
-    else cfg = choose_cfg(n, DEG, ctx->c_override, 0, false);
+    const TabCfg cfg = cfg_for<G>(ctx, bs, n);
     const int c = cfg.c;
-    // 32-bit positions in the sorted list and 31-bit table rows (entry = row | sign << 31)
-    if ((uint64_t)n * (uint64_t)cfg.Wd >= (uint64_t(1) << 32) - 4096 || (uint64_t)bs.n * (uint64_t)cfg.NT >= (uint64_t(1) << 31))
-        return fail(ctx, B200MSM_ERR_ARG, "n = %zu with %d digits per scalar exceeds the 2^32 sorted entries of one call; shard the MSM", n, cfg.Wd);
-    Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
-    int rc = grow_arena(ctx, ln, probe.bytes);
+    // 32-bit positions in the sorted list and 30-bit table rows (reference = row | scratch << 30 | sign << 31)
+    if ((uint64_t)n * (uint64_t)cfg.Wd >= (uint64_t(1) << 32) - 4096 || (uint64_t)bs.n * (uint64_t)cfg.NT >= (uint64_t(1) << 30))
+        return fail(ctx, B200MSM_ERR_ARG, "n = %zu with %d digits per scalar exceeds the 2^32 sorted entries / 2^30 table rows of one call; shard the MSM", n, cfg.Wd);
+    int rc = prepare_kernels<G>(ctx);
     if (rc) return rc;
+    Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
+    if ((rc = grow_arena(ctx, ln, probe.bytes))) return rc;
     Plan p = make_plan<G>(ctx, n, cfg, ln.arena);
     MsmArgs &a = p.a;
+    BaArgs &b = p.b;
     a.bases = bs.pts + offset * AFFW;
     a.base_inf = bs.inf + offset;
     a.tab_stride = (uint32_t)bs.n;
-
-    if ((rc = set_smem(ctx, k_accumulate<G>, AC::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_fold_edges<G>, TC::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_bucket_reduce<G, false>, TC::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_bucket_reduce<G, true>, TC::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_batch_add<G, false>, BaCfg<G>::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_batch_add<G, true>, BaCfg<G>::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_sum<G>, TC::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_horner<G>, TC::TS::SMEM))) return rc;
+    b.bases = a.bases;
 
     uint64_t launches = 0;
     CU(cudaEventRecord(ln.ev[0], st));
@@ -211,72 +225,18 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     launches += 4;
     CU(cudaEventRecord(ln.ev[2], st));
 
+    // bucket accumulation: every team takes its share of the sorted list through all rounds in one launch
+    CU(cudaMemsetAsync(b.ctl, 0, (size_t)BA_CTL_WORDS * 4, st));
+    CU(cudaMemsetAsync(b.bucket_ref, 0xff, (size_t)a.K * 4, st));
+    CU(cudaMemsetAsync(b.bnd_bucket, 0xff, (size_t)2 * b.U * 4, st));
+    const unsigned ba_blocks = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count, (uint64_t)b.U);   // shares are dealt round-robin over the blocks
+    k_batch_add<G><<<ba_blocks, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
+    k_ba_fixup<G><<<1, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
+    launches += 2;
+    CU(cudaEventRecord(ln.ev[3], st));
+
     const unsigned tail_lanes = TC::TPB * 32;
-    const bool batched = ctx->accumulator == 0;
-    uint64_t acc_launches = 0;
-    if (batched) {
-        typedef BaCfg<G> BC;
-        CU(cudaMemsetAsync(p.ba_ctl, 0, (size_t)(3 * p.ba_rounds + 4) * 4, st));
-        BaArgs b;
-        memset(&b, 0, sizeof b);
-        b.K = a.K;
-        b.entries = a.entries;
-        b.bases = a.bases;
-        b.pairs = p.ba_pairs;
-        b.nrounds = p.ba_ctl;
-        b.maxcnt = p.ba_ctl + 1;
-        b.tile_counter = p.ba_ctl + 2 + p.ba_rounds;
-        b.npairs = p.ba_ctl + 2 + 2 * p.ba_rounds;
-        b.bsum = p.bsum;
-        b.nscan = p.nscan;
-        const unsigned plan_blocks = (unsigned)std::min<uint64_t>((p.ba_cap[0] + 255) / 256, (uint64_t)ctx->sm_count * 16);
-        for (int r = 0; r < p.ba_rounds; ++r) {
-            b.round = (uint32_t)r;
-            b.off_cur = a.ba_off[r & 1];
-            b.off_next = a.ba_off[(r + 1) & 1];
-            b.in_pts = a.ba_pts[(r + 1) & 1];
-            b.in_inf = a.ba_inf[(r + 1) & 1];
-            b.out_pts = a.ba_pts[r & 1];
-            b.out_inf = a.ba_inf[r & 1];
-            k_ba_scan_local<<<p.nscan, SCAN_T, 0, st>>>(b);
-            k_ba_scan_bsum<<<1, SCAN_T, 0, st>>>(b);
-            k_ba_scan_add<<<p.nscan, SCAN_T, 0, st>>>(b);
-            if (r == 0) {
-                k_ba_plan<G, true><<<plan_blocks, 256, 0, st>>>(b);
-                k_batch_add<G, true><<<ctx->sm_count * BC::MINB, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
-            } else {
-                k_ba_plan<G, false><<<plan_blocks, 256, 0, st>>>(b);
-                k_batch_add<G, false><<<ctx->sm_count * BC::MINB, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
-            }
-            launches += 5;
-            ++acc_launches;
-        }
-        CU(cudaEventRecord(ln.ev[3], st));
-        k_bucket_reduce<G, true><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
-    } else {
-        CU(cudaMemsetAsync(a.group_counter, 0, 4, st));
-        CU(cudaMemsetAsync(a.edge_bucket, 0xff, (size_t)a.max_chunks * 2 * 4, st));
-        k_accumulate<G><<<ctx->sm_count * AC::MINB, AC::TS::THREADS, AC::TS::SMEM, st>>>(a);
-        launches += 1;
-        acc_launches = 1;
-        CU(cudaEventRecord(ln.ev[3], st));
-        const uint32_t *in_pts = a.edges, *in_key = a.edge_bucket;
-        uint32_t n_in = a.max_chunks;
-        unsigned long long span = a.L;
-        int flip = 0;
-        do {
-            const uint32_t n_out = (n_in + FOLD_GS - 1) / FOLD_GS;
-            span *= FOLD_GS;
-            k_fold_edges<G><<<(n_out + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(
-                a, in_pts, in_key, n_in, a.fold_pts[flip], a.fold_key[flip], n_out, span);
-            ++launches;
-            in_pts = a.fold_pts[flip];
-            in_key = a.fold_key[flip];
-            n_in = n_out;
-            flip ^= 1;
-        } while (n_in > 1);
-        k_bucket_reduce<G, false><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
-    }
+    k_bucket_reduce<G><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
     launches += 1;
     {
         const uint32_t *in = a.segsum;
@@ -299,11 +259,8 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     ++launches;
     CU(cudaEventRecord(ln.ev[4], st));
     CU(cudaMemcpyAsync(ln.h_result, a.result, JACW * 4, cudaMemcpyDeviceToHost, st));
-    ln.ctl_rounds = 0;
-    if (batched && p.ba_rounds <= 32) {
-        CU(cudaMemcpyAsync(ln.h_ctl, p.ba_ctl, (size_t)(3 * p.ba_rounds + 4) * 4, cudaMemcpyDeviceToHost, st));
-        ln.ctl_rounds = p.ba_rounds;
-    }
+    CU(cudaMemcpyAsync(ln.h_ctl, b.ctl, (size_t)BA_CTL_WORDS * 4, cudaMemcpyDeviceToHost, st));
+    ln.ctl_valid = true;
     CU(cudaEventRecord(ln.ev[5], st));
     CU(cudaGetLastError());
 
@@ -312,11 +269,16 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     ln.info[0] = (uint64_t)c;
     ln.info[1] = (uint64_t)a.Wd;
     ln.info[2] = (uint64_t)n * a.Wd;
-    ln.info[3] = acc_launches;
+    ln.info[3] = (uint64_t)b.U;
     ln.info[4] = launches;
     ln.info[5] = (uint64_t)a.W;
     ln.info[6] = (uint64_t)cfg.NT;
-    ln.info[7] = (uint64_t)ctx->accumulator;
+    ln.info[7] = 0;
+    {
+        auto o = [&](const void *q) { return (uint64_t)((const char *)q - ln.arena); };
+        const uint64_t d[16] = {a.K, o(a.offs), o(b.refs[0]), o(b.refs[1]), o(b.scratch), o(b.bucket_ref), o(b.cntv), b.capA, (uint64_t)n * a.Wd, o(a.scalars), (uint64_t)a.W, a.NB, b.U, o(b.bnd_ref), o(b.bnd_bucket), o(b.pairs)};
+        memcpy(ln.dbg, d, sizeof d);
+    }
     return B200MSM_OK;
 }
 

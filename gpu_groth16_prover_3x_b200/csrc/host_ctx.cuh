@@ -12,6 +12,7 @@
 
 #include "../../include/b200_msm.h"
 #include "msm_kernels.cuh"
+#include "batch_affine.cuh"
 #include "util_kernels.cuh"
 
 using namespace mnt753;
@@ -48,14 +49,15 @@ struct Lane {
     char *arena = nullptr;
     size_t arena_bytes = 0;
     uint32_t *h_result = nullptr;  // pinned staging for the Jacobian result
-    uint32_t *h_ctl = nullptr;     // pinned copy of the batched-affine control block (rounds, occupancies, pair counts)
-    int ctl_rounds = 0;            // rounds enqueued by the last MSM (0: not a batched-affine MSM)
+    uint32_t *h_ctl = nullptr;     // pinned copy of the accumulation's statistics (BA_CTL_WORDS: rounds, largest bucket, additions, pairs per round)
+    bool ctl_valid = false;
     uint64_t *user_out = nullptr;
     size_t out_words = 0;
     bool pending = false;
     bool timed = false;
     float ms[6] = {};
     uint64_t info[8] = {};
+    uint64_t dbg[16] = {};         // arena offsets of the last MSM's lists (development introspection, b200msm_internal_debug_*)
 };
 
 // H-polynomial state (fft.cu): tables of the evaluation domain of size 2^logm and three work vectors
@@ -73,7 +75,7 @@ struct b200msm_ctx {
     int device = 0;
     int sm_count = 0;
     int c_override = 0;
-    int accumulator = 0;  // 0: batched-affine rounds (batch_affine.cuh), 1: Jacobian chains (k_accumulate)
+    bool kernels_ready[3] = {false, false, false};  // per group: shared-memory attributes of its kernels set on this device
     size_t table_budget = size_t(32) << 30;  // bytes of window tables per base set (0: never build tables)
     std::vector<BaseSet> sets;
     Lane lanes[NLANES];
@@ -145,14 +147,10 @@ inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bo
 
 struct Plan {
     MsmArgs a;
+    BaArgs b;        // the batched-affine accumulation (batch_affine.cuh)
     size_t bytes;
     uint32_t *bsum;
     uint32_t nscan;
-    // batched-affine rounds
-    uint64_t ba_cap[2] = {0, 0};
-    int ba_rounds = 0;
-    uint4 *ba_pairs = nullptr;
-    uint32_t *ba_ctl = nullptr;
 };
 
 size_t align_up(size_t x, size_t al) { return (x + al - 1) / al * al; }

@@ -115,7 +115,7 @@ __global__ void __launch_bounds__(256) k_mb_lo(uint32_t *out, int iters) {
     if (s == 0x12345678u) out[0] = 1;
 }
 // the engine's own register-resident Montgomery product, iterated
-template <class M, bool RR>
+template <class M>
 __global__ void __launch_bounds__(128) k_mb_fqmul(uint32_t *out, int iters) {
     fq_t x, y;
 #pragma unroll
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(128) k_mb_fqmul(uint32_t *out, int iters) {
     x[NLIMB - 1] &= 0xffffu;
     y[NLIMB - 1] &= 0xffffu;
     for (int it = 0; it < iters; ++it) {
-        if (RR) fq_mul_rr<M>(x, x, y); else fq_mul<M>(x, x, y);
+        fq_mul<M>(x, x, y);
     }
     uint32_t s = 0;
 #pragma unroll
@@ -185,7 +185,7 @@ int b200msm_create(int curve, int device, b200msm_ctx **out) {
         ok = ok && cudaStreamCreateWithFlags(&ln.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
         for (int e = 0; e <= NCOPY && ok; ++e) ok = cudaEventCreateWithFlags(&ln.ev_copy[e], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_result, 3 * 3 * NLIMB * 4) == cudaSuccess;
-        ok = ok && cudaMallocHost(&ln.h_ctl, (3 * 32 + 8) * 4) == cudaSuccess;
+        ok = ok && cudaMallocHost(&ln.h_ctl, BA_CTL_WORDS * 4) == cudaSuccess;
         if (!ok) { b200msm_destroy(ctx); return B200MSM_ERR_CUDA; }
     }
     *out = ctx;
@@ -343,15 +343,6 @@ int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream) {
     return B200MSM_OK;
 }
 
-int b200msm_set_accumulator(b200msm_ctx *ctx, int mode) {
-    if (!ctx) return B200MSM_ERR_ARG;
-    if (mode != 0 && mode != 1) return fail(ctx, B200MSM_ERR_ARG, "accumulator mode %d (0: batched affine, 1: Jacobian chains)", mode);
-    for (int i = 0; i < NLANES; ++i)
-        if (ctx->lanes[i].pending) return fail(ctx, B200MSM_ERR_ARG, "lane %d still has an un-waited MSM", i);
-    ctx->accumulator = mode;
-    return B200MSM_OK;
-}
-
 int b200msm_set_table_budget(b200msm_ctx *ctx, size_t max_bytes_per_set) {
     if (!ctx) return B200MSM_ERR_ARG;
     ctx->table_budget = max_bytes_per_set;
@@ -383,19 +374,31 @@ int b200msm_last_rounds(b200msm_ctx *ctx, int lane, uint64_t info[4], uint32_t *
     if (lane < 0 || lane >= NLANES || !info) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
     const Lane &ln = ctx->lanes[lane];
     if (ln.pending) return fail(ctx, B200MSM_ERR_ARG, "lane %d still has an un-waited MSM", lane);
-    const int R = ln.ctl_rounds;
     memset(info, 0, 4 * sizeof(uint64_t));
-    if (R == 0) return B200MSM_OK;
-    const uint32_t *ctl = ln.h_ctl;   // nrounds | maxcnt[R + 1] | tile_counter[R] | npairs[R]
+    if (!ln.ctl_valid) return B200MSM_OK;
+    const uint32_t *ctl = ln.h_ctl;   // BA_CTL_WORDS: rounds | largest bucket | additions | - | pairs of round r ...
     info[0] = ctl[0];
-    info[1] = (uint64_t)R;
+    info[1] = ln.info[3];
     info[2] = ctl[1];
-    uint64_t adds = 0;
-    for (int r = 0; r < R; ++r) {
-        adds += ctl[2 + 2 * R + r];
-        if (pairs_per_round && (size_t)r < max_rounds) pairs_per_round[r] = ctl[2 + 2 * R + r];
-    }
-    info[3] = adds;
+    info[3] = ctl[2];
+    for (uint32_t r = 0; r < ctl[0] && r < (uint32_t)(BA_CTL_WORDS - 4); ++r)
+        if (pairs_per_round && (size_t)r < max_rounds) pairs_per_round[r] = ctl[4 + r];
+    return B200MSM_OK;
+}
+
+// development introspection (not declared in the public header): arena offsets of the last MSM of a lane, raw reads
+int b200msm_internal_debug_layout(b200msm_ctx *ctx, int lane, uint64_t dbg[16]) {
+    if (!ctx || lane < 0 || lane >= NLANES) return B200MSM_ERR_ARG;
+    memcpy(dbg, ctx->lanes[lane].dbg, sizeof ctx->lanes[lane].dbg);
+    return B200MSM_OK;
+}
+int b200msm_internal_debug_read(b200msm_ctx *ctx, int lane, uint64_t offset, uint64_t bytes, void *out) {
+    if (!ctx || lane < 0 || lane >= NLANES) return B200MSM_ERR_ARG;
+    Lane &ln = ctx->lanes[lane];
+    if (offset + bytes > ln.arena_bytes) return fail(ctx, B200MSM_ERR_ARG, "debug read beyond the arena");
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(out, ln.arena + offset, bytes, cudaMemcpyDeviceToHost));
     return B200MSM_OK;
 }
 
@@ -409,7 +412,7 @@ int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[
 
 int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     if (!ctx) return B200MSM_ERR_ARG;
-    if (!gops || iters <= 0 || kind < 0 || kind > 18) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
+    if (!gops || iters <= 0 || kind < 0 || kind > 18 || kind == 3) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
     CU(cudaSetDevice(ctx->device));
     if (kind >= 15) {  // register multiplier at 4 (kind 15), 8 (16) or 12 (17) warps per SM: does ONE warp per scheduler fill the pipe?
         if (kind > 17) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
@@ -421,7 +424,7 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
         const int nb = ctx->sm_count * (kind - 14);
         for (int rep = 0; rep < 2; ++rep) {
             CU(cudaEventRecord(a0, 0));
-            k_mb_fqmul<ModA, false><<<nb, 128>>>(dd, iters);
+            k_mb_fqmul<ModA><<<nb, 128>>>(dd, iters);
             CU(cudaEventRecord(a1, 0));
             CU(cudaEventSynchronize(a1));
         }
@@ -470,9 +473,8 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
         if (kind == 0) { k_mb_wide<<<blocks, 256>>>(d, iters); ops = double(blocks) * 256 * iters * MB_CHAINS; }
         else if (kind == 1) { k_mb_lo<<<blocks, 256>>>(d, iters); ops = double(blocks) * 256 * iters * MB_CHAINS; }
         else {
-            if (kind == 3) k_mb_fqmul<ModA, true><<<blocks, 128>>>(d, iters);
-            else if (ctx->curve == B200MSM_MNT4753) k_mb_fqmul<ModA, false><<<blocks, 128>>>(d, iters);
-            else k_mb_fqmul<ModB, false><<<blocks, 128>>>(d, iters);
+            if (ctx->curve == B200MSM_MNT4753) k_mb_fqmul<ModA><<<blocks, 128>>>(d, iters);
+            else k_mb_fqmul<ModB><<<blocks, 128>>>(d, iters);
             ops = double(blocks) * 128 * iters;
         }
         CU(cudaEventRecord(e1, 0));

@@ -6,11 +6,8 @@
 //   k_count           signed-digit recode, histogram of (window, bucket) keys
 //   k_scan_*          exclusive prefix sum of the histogram
 //   k_scatter         single-pass radix (counting) sort: point indices grouped by (window, bucket)
-//   k_accumulate      bucket accumulation: each lane walks a fixed-length chunk of the sorted list,
-//                     streaming affine bases from HBM (128-bit cp.async into the team slab), one
-//                     mixed addition per entry; runs that cover a whole bucket are written straight
-//                     to the bucket array, runs cut by a chunk border go to an edge list
-//   k_fold_edges      hierarchical (32-ary) fold of the edge partial sums of buckets that span chunks
+//   k_batch_add       bucket accumulation (batch_affine.cuh): rounds of pairwise affine additions, one
+//   k_ba_fixup        persistent launch, every team takes its share of the sorted list through all rounds
 //   k_bucket_reduce   per (window, segment): running-sum reduction  sum_b b*B_b  of a bucket segment
 //   k_sum             plain segmented sums (segment sums -> window sums)
 //   k_horner          window combine: result = sum_w 2^(c*w) * S_w
@@ -23,8 +20,6 @@
 
 namespace mnt753 {
 
-constexpr uint32_t EDGE_NONE = 0xffffffffu;
-
 struct MsmArgs {
     // problem
     uint32_t n;        // number of points
@@ -35,8 +30,6 @@ struct MsmArgs {
     uint32_t tab_stride;  // points per precomputed table (table t holds 2^(c*W*t) * P_i), see BaseSet
     uint32_t NB;       // buckets per set = 2^(c-1)
     uint32_t K;        // W * NB
-    uint32_t L;        // sorted-list entries per lane chunk
-    uint32_t max_chunks;
     uint32_t m;        // bucket-reduce segment length (power of two)
     uint32_t nseg;     // NB / m
     // buffers
@@ -47,22 +40,14 @@ struct MsmArgs {
     uint32_t *offs;             // K + 1
     uint32_t *cursor;           // K
     uint32_t *entries;          // n * Wd : table row | sign << 31
-    uint32_t *buckets;          // K Jacobian points (3*DEG*24 words each)
-    uint32_t *edges;            // max_chunks * 2 Jacobian points
-    uint32_t *edge_bucket;      // max_chunks * 2, preset to EDGE_NONE by the host
-    uint32_t *fold_pts[2];      // ping-pong edge arrays of the fold levels
-    uint32_t *fold_key[2];
     uint32_t *segsum;           // W * nseg Jacobian points
     uint32_t *tmp_a, *tmp_b;    // scratch point arrays for k_sum levels
     uint32_t *winsum;           // W Jacobian points
     uint32_t *result;           // 1 Jacobian point
-    uint32_t *group_counter;    // dynamic work counter for k_accumulate
-    // batched-affine accumulation (batch_affine.cuh): ping-pong round outputs; after the last executed round
-    // r = *ba_nrounds the bucket b holds at most one affine point, ba_pts[(r-1)&1][ba_off[r&1][b]]
-    uint32_t *ba_pts[2];
-    uint8_t *ba_inf[2];
-    uint32_t *ba_off[2];        // ba_off[0] == offs
-    uint32_t *ba_nrounds;
+    // what the batched-affine accumulation (batch_affine.cuh) leaves of every bucket: a reference to one affine
+    // point -- a table row (bit 31: negated), a slot of the scratch array (bit 30), or 0xffffffff for nothing
+    const uint32_t *bucket_ref;
+    const uint32_t *ba_scratch;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -307,103 +292,6 @@ __device__ __forceinline__ uint32_t bucket_of(const uint32_t *offs, uint32_t n, 
 }
 
 // ------------------------------------------------------------------------------------------
-// bucket accumulation
-template <class G>
-struct AccCfg {
-    static constexpr int DEG = G::F::DEG;
-    static constexpr int NSLOT = 8;
-    static constexpr int TPB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 1);
-    static constexpr int MINB = DEG == 1 ? 3 : (DEG == 2 ? 2 : 3);
-    typedef TeamSetup<G, NSLOT, TPB> TS;
-};
-
-template <class G>
-__global__ void __launch_bounds__(AccCfg<G>::TS::THREADS, AccCfg<G>::MINB) k_accumulate(MsmArgs a) {
-    typedef typename G::F F;
-    typedef AccCfg<G> C;
-    constexpr int DEG = F::DEG;
-    constexpr int AFFW = 2 * DEG * NLIMB, JACW = 3 * DEG * NLIMB, EW = DEG * NLIMB;
-    extern __shared__ uint4 smem[];
-    __shared__ uint32_t s_flags[C::TPB][4];
-    __shared__ uint32_t s_group[C::TPB];
-    int team;
-    const Team<F> T = C::TS::make(smem, s_flags, team);
-    const int lane = threadIdx.x & 31;
-    const PtSlots s = {0, 1, 2, 3, 4, 4, 5, 6, 7};
-
-    const uint32_t E = a.offs[a.K];
-    const uint32_t nchunks = (uint32_t)(((uint64_t)E + a.L - 1) / a.L);
-    const uint32_t ngroups = (nchunks + 31) / 32;
-
-    for (;;) {
-        T.sync();
-        if (T.comp == 0 && lane == 0) s_group[team] = atomicAdd(a.group_counter, 1u);
-        T.sync();
-        const uint32_t grp = s_group[team];
-        if (grp >= ngroups) break;
-        const uint32_t chunk = grp * 32 + lane;
-        const bool has_chunk = chunk < nchunks;
-        const uint32_t cstart = has_chunk ? chunk * a.L : 0u;
-        const uint32_t cend = has_chunk ? (uint32_t)min((uint64_t)cstart + a.L, (uint64_t)E) : 0u;
-        uint32_t pos = cstart;
-        uint32_t b = 0, bstart = 0, bend = 0;
-        if (has_chunk) {
-            b = bucket_of(a.offs, a.K, cstart);
-            bstart = a.offs[b];
-            bend = a.offs[b + 1];
-        }
-        bool acc_inf = true;
-        bool neg_next = false;
-        {
-            const bool act = has_chunk && pos < cend;
-            uint32_t e = act ? a.entries[pos] : 0u;
-            neg_next = e >> 31;
-            const uint32_t *src = a.bases + (size_t)(e & 0x7fffffffu) * AFFW;
-            g2s_async(T, s.X2, src, act);
-            g2s_async(T, s.Y2, src + EW, act);
-        }
-        auto flush = [&](bool pred) {
-            // run of bucket b inside this chunk is finished
-            const bool complete = bstart >= cstart && bend <= cend;
-            const uint32_t which = bstart < cstart ? 0u : 1u;
-            uint32_t *dst = complete ? a.buckets + (size_t)b * JACW : a.edges + ((size_t)chunk * 2 + which) * JACW;
-            if (pred && !complete && T.comp == 0) a.edge_bucket[2 * chunk + which] = b;
-            T.set_zero(s.Z1, pred && acc_inf);
-            store_jac(T, dst, s.X1, s.Y1, s.Z1, pred);
-        };
-        for (uint32_t step = 0; step < a.L; ++step) {
-            const bool active = has_chunk && pos < cend;
-            if (!team_any(active)) break;
-            const bool fl = active && pos == bend;
-            if (team_any(fl)) {
-                flush(fl);
-                if (fl) {
-                    acc_inf = true;
-                    do { ++b; } while (a.offs[b + 1] <= pos);
-                    bstart = a.offs[b];
-                    bend = a.offs[b + 1];
-                }
-            }
-            const bool neg = neg_next;
-            async_wait_all();
-            Ec<F>::madd_head(T, s, neg, active, acc_inf);
-            {
-                const bool act = active && pos + 1 < cend;
-                uint32_t e = act ? a.entries[pos + 1] : 0u;
-                neg_next = e >> 31;
-                const uint32_t *src = a.bases + (size_t)(e & 0x7fffffffu) * AFFW;
-                g2s_async(T, s.X2, src, act);
-                g2s_async(T, s.Y2, src + EW, act);
-            }
-            Ec<F>::madd_tail(T, s, neg, active, acc_inf);
-            if (active) ++pos;
-        }
-        async_wait_all();
-        flush(has_chunk && cend > cstart);
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // generic tail kernels: 12 slots  TOT(0-2) RUN(3-5) Q(6-8) T(9-11)
 template <class G>
 struct TailCfg {
@@ -413,64 +301,9 @@ struct TailCfg {
     typedef TeamSetup<G, NSLOT, TPB> TS;
 };
 
-// Hierarchical fold of the edge partials.  Level l >= 1 group g covers the sorted-list range
-// [g*span, (g+1)*span) with span = L * FOLD_GS^l; its inputs are the (at most two per child) edge
-// partials that its FOLD_GS children of level l-1 emitted, visited in list order so that all
-// partials of one bucket are consecutive.  One lane per group: runs of equal bucket id are summed;
-// a run whose bucket lies entirely inside the group is final (-> bucket array), otherwise it is
-// re-emitted as this group's own prefix (slot 0) / suffix (slot 1) edge for the next level.  The
-// depth is log_32(#chunks) and no lane ever walks more than 2*FOLD_GS partials, whatever the bucket
-// occupancy (a uniform scalar always has a giant top-window bucket: r ~ 1.77 * 2^752).
-constexpr uint32_t FOLD_GS = 32;
+// running-sum reduction of one bucket segment per lane; out[w*nseg + seg] = sum_{j<m} (seg*m+j+1) * B[w][seg*m+j].
+// A bucket is one affine point (or nothing), given by reference: see MsmArgs::bucket_ref.
 template <class G>
-__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_fold_edges(MsmArgs a, const uint32_t *in_pts, const uint32_t *in_key,
-                                                                        uint32_t n_in, uint32_t *out_pts, uint32_t *out_key,
-                                                                        uint32_t n_out, unsigned long long span) {
-    typedef typename G::F F;
-    typedef TailCfg<G> C;
-    constexpr int JACW = 3 * F::DEG * NLIMB;
-    extern __shared__ uint4 smem[];
-    __shared__ uint32_t s_flags[C::TPB][4];
-    int team;
-    const Team<F> T = C::TS::make(smem, s_flags, team);
-    const int lane = threadIdx.x & 31;
-    const PtSlots s = {0, 1, 2, 6, 7, 8, 9, 10, 11};
-    const uint32_t g = (blockIdx.x * C::TPB + team) * 32 + lane;
-    const bool valid = g < n_out;
-    const unsigned long long E = a.offs[a.K];
-    const unsigned long long gstart = (unsigned long long)g * span, gend = min(gstart + span, E);
-    if (valid && T.comp == 0) { out_key[2 * g] = EDGE_NONE; out_key[2 * g + 1] = EDGE_NONE; }
-    uint32_t cur = EDGE_NONE;
-    auto flush = [&](bool pred) {
-        const uint32_t b = pred ? cur : 0u;
-        const uint32_t bstart = a.offs[b], bend = a.offs[b + 1];
-        const bool complete = bstart >= gstart && bend <= gend;
-        const uint32_t which = bstart < gstart ? 0u : 1u;
-        uint32_t *dst = complete ? a.buckets + (size_t)b * JACW : out_pts + ((size_t)g * 2 + which) * JACW;
-        if (pred && !complete && T.comp == 0) out_key[2 * g + which] = b;
-        store_jac(T, dst, s.X1, s.Y1, s.Z1, pred);
-    };
-    for (uint32_t i = 0; i < 2 * FOLD_GS; ++i) {
-        const uint32_t slot = (g * FOLD_GS) * 2 + i;
-        const uint32_t key = (valid && slot < 2 * n_in) ? in_key[slot] : EDGE_NONE;
-        const bool active = key != EDGE_NONE;
-        if (!team_any(active)) continue;
-        const bool newrun = active && key != cur;
-        const bool fl = newrun && cur != EDGE_NONE;
-        if (team_any(fl)) flush(fl);
-        T.set_zero(s.Z1, newrun);
-        if (newrun) cur = key;
-        load_jac(T, s.X2, s.Y2, s.Z2, in_pts + (size_t)slot * JACW, active);
-        T.set_zero(s.Z2, !active);
-        Ec<F>::add(T, s, active);
-    }
-    flush(cur != EDGE_NONE);
-}
-
-// running-sum reduction of one bucket segment per lane; out[w*nseg + seg] = sum_{j<m} (seg*m+j+1) * B[w][seg*m+j]
-// AFF: buckets come from the batched-affine rounds (one affine point or nothing per bucket, mixed
-// additions); otherwise from the Jacobian bucket array written by k_accumulate / k_fold_edges.
-template <class G, bool AFF>
 __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_bucket_reduce(MsmArgs a) {
     typedef typename G::F F;
     typedef TailCfg<G> C;
@@ -485,34 +318,19 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_bucket_reduce(MsmAr
     const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + lane;
     const bool valid = id < (uint32_t)a.W * a.nseg;
     const uint32_t w = valid ? id / a.nseg : 0u, seg = valid ? id % a.nseg : 0u;
-    const uint32_t *off = a.offs, *pts = nullptr;
-    const uint8_t *pinf = nullptr;
-    if (AFF) {
-        const uint32_t nr = *a.ba_nrounds;
-        off = a.ba_off[nr & 1u];
-        pts = a.ba_pts[(nr - 1u) & 1u];
-        pinf = a.ba_inf[(nr - 1u) & 1u];
-    }
     T.set_zero(tot.Z1);
     T.set_zero(run.Z1);
     bool run_inf = true;
     for (int j = (int)a.m - 1; j >= 0; --j) {
         const uint32_t key = w * a.NB + seg * a.m + (uint32_t)j;
-        const uint32_t o = valid ? off[key] : 0u;
-        bool ne = valid && off[key + 1] > o;
-        if (AFF) {
-            ne = ne && !pinf[o];
-            if (team_any(ne)) {
-                g2s(T, run.X2, pts + (size_t)o * AFFW, ne);
-                g2s(T, run.Y2, pts + (size_t)o * AFFW + EW, ne);
-                T.sync();
-                Ec<F>::madd(T, run, false, ne, run_inf);
-            }
-        } else if (team_any(ne)) {
-            load_jac(T, run.X2, run.Y2, run.Z2, a.buckets + (size_t)key * JACW, ne);
-            T.set_zero(run.Z2, !ne);
-            Ec<F>::add(T, run, ne);
-            run_inf = run_inf && !ne;
+        const uint32_t ref = valid ? a.bucket_ref[key] : 0xffffffffu;
+        const bool ne = ref != 0xffffffffu;
+        if (team_any(ne)) {
+            const uint32_t *src = ((ref & 0x40000000u) ? a.ba_scratch : a.bases) + (size_t)(ref & 0x3fffffffu) * AFFW;
+            g2s(T, run.X2, src, ne);
+            g2s(T, run.Y2, src + EW, ne);
+            T.sync();
+            Ec<F>::madd(T, run, (ref >> 31) != 0u, ne, run_inf);
         }
         if (team_any(!run_inf)) {
             T.copy(tot.X2, run.X1); T.copy(tot.Y2, run.Y1); T.copy(tot.Z2, run.Z1);

@@ -65,7 +65,6 @@ def load_library():
     lib.b200msm_set_stream.argtypes = [vp, ci, vp]
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
     lib.b200msm_set_table_budget.argtypes = [vp, sz]
-    lib.b200msm_set_accumulator.argtypes = [vp, ci]
     lib.b200msm_scalar_mul.argtypes = [vp, ci, vp, vp, vp]
     lib.b200msm_key_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
     lib.b200msm_key_load_file.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(vp)]
@@ -262,8 +261,7 @@ class MsmContext:
         self._check(self.lib.b200msm_last_timings(self._h, lane, ms, info))
         d = {k: float(ms[i]) for i, k in enumerate(self.PHASES)}
         d.update(window_bits=int(info[0]), windows=int(info[1]), entries=int(info[2]),
-                 accumulate_launches=int(info[3]), kernel_launches=int(info[4]), bucket_sets=int(info[5]),
-                 tables=int(info[6]), accumulator=int(info[7]))
+                 shares=int(info[3]), kernel_launches=int(info[4]), bucket_sets=int(info[5]), tables=int(info[6]))
         return d
 
     def scalar_mul(self, group, affine, k_mont):
@@ -331,10 +329,6 @@ class MsmContext:
         self._check(self.lib.b200msm_compute_h_timings(self._h, ms))
         return {"compute_h_ms": float(ms[0]), "tables_ms": float(ms[1])}
 
-    def set_accumulator(self, mode):
-        """0: batched-affine rounds (default), 1: Jacobian mixed-addition chains."""
-        self._check(self.lib.b200msm_set_accumulator(self._h, mode))
-
     def set_table_budget(self, max_bytes_per_set):
         """Byte budget of the window tables built at upload time (0: none), see include/b200_msm.h."""
         self._check(self.lib.b200msm_set_table_budget(self._h, max_bytes_per_set))
@@ -349,7 +343,7 @@ class MsmContext:
         info = (ctypes.c_uint64 * 4)()
         pairs = (ctypes.c_uint32 * 32)()
         self._check(self.lib.b200msm_last_rounds(self._h, lane, info, pairs, 32))
-        return dict(rounds=int(info[0]), rounds_enqueued=int(info[1]), max_bucket_occupancy=int(info[2]),
+        return dict(rounds=int(info[0]), shares=int(info[1]), max_bucket_occupancy=int(info[2]),
                     additions=int(info[3]), pairs_per_round=[int(x) for x in pairs[:int(info[0])]])
 
     def microbench(self, kind, iters=4096):

@@ -63,3 +63,48 @@ def random_scalars(curve, n, seed):
         out[filled:filled + k] = x[:k]
         filled += k
     return out.reshape(-1)
+
+
+def write_instance(curve, d, directory, device=0, seed=7, infinities=(3, 5)):
+    """Write a Groth16 instance of the reference's on-disk formats (SURVEY.md appendix A;
+    generate_parameters.cpp:59-108, main.cpp:35-85) with m = d + 1 variables:
+        <curve>-parameters   u64 d, u64 m, A[m+1] G1, B1[m+1] G1, B2[m+1] G2, L[m-1] G1, H[d] G1
+        <curve>-input        w[m+1] (w[0] = 1), ca[d+1], cb[d+1], cc[d+1], r   -- Fr, Montgomery limbs
+    The five queries are structured base sets P0 + i*Q generated in HBM by the engine (distinct P0, Q per
+    query, all in the prime-order subgroup) with the points at `infinities` of A, B1 and B2 replaced by the
+    encoding of infinity (all-zero), as real proving keys have; the witness and the QAP evaluations are uniform
+    field elements.  Any prover that follows the reference's `compute` semantics -- the reference CPU prover
+    `main` included -- maps these two files to one well-defined proof; that is all the parity check needs, and it
+    replaces three minutes of `generate_parameters` at the default size (d = 2^20 - 1) by seconds.
+    -> (parameters path, input path)."""
+    import os
+
+    from .engine import G1, G2, MsmContext, degree
+    name = "MNT4753" if curve == MNT4753 else "MNT6753"
+    m = d + 1
+    r = fr_modulus(curve)
+    ppath, ipath = os.path.join(directory, name + "-parameters"), os.path.join(directory, name + "-input")
+    with MsmContext(curve, device) as ctx:
+        ctx.set_table_budget(0)                    # points only: no window tables for a set that is downloaded at once
+        with open(ppath + ".tmp", "wb") as f:
+            np.array([d, m], np.uint64).tofile(f)
+            for q, (group, n) in enumerate(((G1, m + 1), (G1, m + 1), (G2, m + 1), (G1, m - 1), (G1, d))):
+                k0, k1 = base_seed_scalars(curve, 2000001 + 16 * seed + 2 * q, 2000002 + 16 * seed + 2 * q)
+                slot = ctx.synthetic_bases(group, n, k0, k1)
+                pts = ctx.download_bases(slot, 0, n).reshape(n, 24 * degree(curve, group))
+                ctx.free_bases(slot)
+                if q < 3:
+                    for i in infinities:
+                        if i < n:
+                            pts[i] = 0
+                pts.tofile(f)
+    os.replace(ppath + ".tmp", ppath)
+    with open(ipath + ".tmp", "wb") as f:
+        w = random_scalars(curve, m + 1, 9000 + seed).reshape(m + 1, 12)
+        w[0] = int_to_limbs(R % r)                 # w[0] = 1 in Montgomery form
+        w.tofile(f)
+        for j in range(3):
+            random_scalars(curve, d + 1, 9100 + 4 * seed + j).tofile(f)
+        random_scalars(curve, 1, 9200 + seed).tofile(f)
+    os.replace(ipath + ".tmp", ipath)
+    return ppath, ipath

@@ -160,24 +160,21 @@ void b200msm_pinned_free(void *p);
 int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream);
 
 /* Tuning / introspection. */
-/* Bucket accumulation algorithm: 0 (default) = rounds of pairwise AFFINE additions sharing one field
- * inversion per tile (6 field multiplications per addition), 1 = per-lane Jacobian mixed-addition chains
- * (11 per addition; the round-1 baseline, kept for A/B measurement).  Results are identical. */
-int b200msm_set_accumulator(b200msm_ctx *ctx, int mode);
 /* Window width for MSMs and for the tables of base sets uploaded afterwards; 0 = automatic.  An MSM
  * whose forced width differs from the one its base set's tables were built for ignores the tables. */
 int b200msm_set_window_bits(b200msm_ctx *ctx, int c);
 /* Device time of the phases of the most recent completed MSM on `lane`, milliseconds, measured with
  * CUDA events on the launching stream: [0] total, [1] H2D scalars, [2] recode+sort,
- * [3] bucket accumulation (k_accumulate), [4] bucket reduction + window combine, [5] D2H result.
+ * [3] bucket accumulation (k_batch_add + k_ba_fixup), [4] bucket reduction + window combine, [5] D2H result.
  * info[0] = window bits c, [1] = signed digits (windows) per scalar, [2] = sorted entries,
- * [3] = accumulation launches (batched-affine rounds enqueued, or 1), [4] = total kernel launches of the
- * MSM, [5] = bucket sets G, [6] = window tables used NT, [7] = accumulator mode. */
+ * [3] = shares the sorted list was cut into (teams of the accumulation kernel), [4] = total kernel launches of the
+ * MSM, [5] = bucket sets G, [6] = window tables used NT, [7] = 0. */
 int b200msm_last_timings(b200msm_ctx *ctx, int lane, float ms[6], uint64_t info[8]);
 
-/* Batched-affine rounds of the most recent completed MSM on `lane`: info[0] = rounds executed, [1] = rounds
- * enqueued (worst case), [2] = largest bucket occupancy after the sort, [3] = affine additions performed;
- * pairs_per_round (may be NULL) receives the additions of each round.  All zero for the Jacobian accumulator. */
+/* Batched-affine rounds of the most recent completed MSM on `lane`: info[0] = rounds executed (the largest number
+ * over the shares: every team runs its own buckets through their rounds), [1] = shares, [2] = largest bucket (or
+ * piece of a split bucket) after the sort, [3] = affine additions performed; pairs_per_round (may be NULL) receives
+ * the additions of each round summed over the shares. */
 int b200msm_last_rounds(b200msm_ctx *ctx, int lane, uint64_t info[4], uint32_t *pairs_per_round, size_t max_rounds);
 
 /* Synthetic microbenchmarks used by bench.py for the roofline denominator: runs `iters`
@@ -187,7 +184,7 @@ int b200msm_last_rounds(b200msm_ctx *ctx, int lane, uint64_t info[4], uint32_t *
  *           on B200: 32 per clock per SM), 1 = IMAD (mad.lo, 64 per clock per SM),
  *       2 = the engine's own Fq Montgomery multiplication (32-bit CIOS on IMAD.WIDE.U32.X carry
  *           chains; returns 10^9 modmul/s),
- *       3 = the reduced-radix (29-bit limbs, carry-free IMAD.WIDE.U32) experiment, for comparison;
+ *       (3 was the reduced-radix experiment, now tools/experiments/fq_experiments.cuh; rejected);
  *       4, 5, 6 = latency of one Fq inversion by a single thread, in MICROSECONDS (not a rate): the engine's
  *           fq_inv, the plain binary gcd, the approximation-based fast path alone (fails if it ever needs
  *           the fallback);

@@ -55,7 +55,8 @@ def emu():
     extra = os.environ.get("EMU_CFLAGS", "").split()   # e.g. -DMNT753_MUL_ROLL=8 to emulate a multiplier variant
     so = os.path.join(d, "libemu%s.so" % ("_" + "".join(c for c in "".join(extra) if c.isalnum()) if extra else ""))
     srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f)
-                                            for f in ("prim.cuh", "fq.cuh", "fe.cuh", "ec.cuh", "curves.cuh", "batch_affine.cuh", "fq_fp64.cuh")]
+                                            for f in ("prim.cuh", "fq.cuh", "fe.cuh", "ec.cuh", "curves.cuh", "batch_affine.cuh")]
+    srcs += [os.path.join(ROOT, "tools", "experiments", f) for f in ("fq_fp64.cuh", "fq_experiments.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU"] + extra + ["-x", "c++",
                         srcs[0], "-o", so], check=True)

@@ -9,7 +9,8 @@
 
 #include "../../gpu_groth16_prover_3x_b200/csrc/curves.cuh"
 #include "../../gpu_groth16_prover_3x_b200/csrc/batch_affine.cuh"
-#include "../../gpu_groth16_prover_3x_b200/csrc/fq_fp64.cuh"
+#include "../../tools/experiments/fq_fp64.cuh"
+#include "../../tools/experiments/fq_experiments.cuh"
 
 using namespace mnt753;
 

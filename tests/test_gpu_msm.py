@@ -133,26 +133,45 @@ def test_window_tables(ctxs, oracle, golden, curve, group):
 
 
 @pytest.mark.parametrize("curve,group", CG)
-def test_jacobian_chain_accumulator(ctxs, oracle, golden, curve, group):
-    """The round-1 baseline accumulator (per-lane Jacobian mixed-addition chains + edge fold) stays
-    selectable for A/B measurement and must give the same points as the batched-affine rounds."""
-    z = golden["msm_vectors"]
-    key = "c%d_g%d" % (curve, group)
-    bases, sc = z[key + "_bases"], z[key + "_scalars"]
+def test_giant_buckets_are_split_and_fixed_up(ctxs, oracle, curve, group):
+    """The accumulation cuts the sorted list into shares at bucket boundaries, except for a bucket larger than
+    half a share, whose pieces are summed by k_ba_fixup.  Scalars with few distinct values put thousands of points
+    into one bucket per window (as the 0/1 wires of a real witness do): equal scalars (one giant bucket per window,
+    repeated points doubling inside it), two values, and P / -P pairs that cancel inside a giant bucket."""
+    n = 3000
+    deg = po.degree(curve, group)
+    bases = oracle.gen_bases(curve, group, n)
+    sc = po.gen_scalars(curve, n, 11).reshape(n, 12)
     ctx = ctxs[curve]
-    slot = ctx.upload_bases(group, bases)
-    try:
-        ctx.set_accumulator(1)
-        for c in (0, 6, 13):
-            ctx.set_window_bits(c)
-            for n in (257, 33, 1):
-                got = affine(oracle, curve, group, ctx.msm(slot, sc[:n * 12], n))
-                assert (got == z["%s_n%d_out" % (key, n)]).all(), (c, n)
-                assert ctx.last_timings()["accumulator"] == 1
-    finally:
-        ctx.set_accumulator(0)
-        ctx.set_window_bits(0)
-        ctx.free_bases(slot)
+    cases = {}
+    same = sc.copy(); same[:] = sc[0]
+    cases["equal"] = (bases, same.reshape(-1))
+    two = sc.copy(); two[::2] = sc[1]; two[1::2] = sc[2]
+    cases["two values"] = (bases, two.reshape(-1))
+    mixed = sc.copy(); mixed[: n // 2] = sc[3]
+    cases["half equal"] = (bases, mixed.reshape(-1))
+    # every base twice in a row: (P_i, P_i) doubles inside a bucket
+    dup = bases.reshape(n, 24 * deg).copy(); dup[1::2] = dup[0::2]
+    cases["repeated points"] = (dup.reshape(-1), same.reshape(-1))
+    # P_i followed by -P_i with the same scalar: the pair cancels to infinity
+    neg = bases.reshape(n, 24 * deg).copy()
+    for i in range(0, n - 1, 2):
+        y = neg[i, 12 * deg:].copy()
+        neg[i + 1, :12 * deg] = neg[i, :12 * deg]
+        neg[i + 1, 12 * deg:] = oracle.field_op(curve, 0 if group == 1 else 1, 5, y)
+    cases["cancelling pairs"] = (neg.reshape(-1), same.reshape(-1))
+    for c in (0, 9):
+        ctx.set_window_bits(c)
+        try:
+            for name, (b, s) in cases.items():
+                slot = ctx.upload_bases(group, b)
+                got = affine(oracle, curve, group, ctx.msm(slot, s, n))
+                want, _ = oracle.msm(curve, group, b, s)
+                assert (got == want).all(), (name, c)
+                assert ctx.last_rounds()["max_bucket_occupancy"] >= 256, name     # larger than half a share: cut and fixed up
+                ctx.free_bases(slot)
+        finally:
+            ctx.set_window_bits(0)
 
 
 def test_async_lanes_and_shards(ctxs, oracle):

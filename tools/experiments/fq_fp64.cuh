@@ -20,7 +20,7 @@
 // Per product: 2 * 15 * 15 * (K + 1) / 2 limb products = 3 FP64 + 2 ALU instructions each, against
 // 576 (K + 1) + 24 quarter-rate IMAD.WIDE of the integer form.  Results are bit-identical to fq_dot.
 #pragma once
-#include "fq.cuh"
+#include "../../gpu_groth16_prover_3x_b200/csrc/fq.cuh"
 
 #ifdef MNT753_HOST_EMU
 #include <cstring>

@@ -7,7 +7,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
-#include "../gpu_groth16_prover_3x_b200/csrc/fq_fp64.cuh"
+#include "experiments/fq_fp64.cuh"
+#include "experiments/fq_experiments.cuh"
 
 using namespace mnt753;
 

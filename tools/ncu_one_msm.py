@@ -13,8 +13,6 @@ group = int(sys.argv[3]) if len(sys.argv) > 3 else 1
 reps = int(sys.argv[4]) if len(sys.argv) > 4 else 2
 n = 1 << log_n
 ctx = pkg.MsmContext(curve, 0)
-if os.environ.get("B200MSM_ACC"):
-    ctx.set_accumulator(int(os.environ["B200MSM_ACC"]))
 if os.environ.get("B200MSM_C"):
     ctx.set_window_bits(int(os.environ["B200MSM_C"]))
 k0, k1 = synthetic.base_seed_scalars(curve)
