@@ -20,6 +20,9 @@
 // used in place.
 #pragma once
 #include "fq.cuh"
+#ifndef MNT753_HOST_EMU
+#include "fq_inv_coop.cuh"
+#endif
 
 namespace mnt753 {
 
@@ -284,27 +287,38 @@ struct Team {
         mul(d, t0, t1);
     }
     // d = 1 / a for the element of LANE 0 only (other lanes: unspecified); a != 0.  t0, t1 scratch, all
-    // four slots distinct.  One binary-gcd inversion in Fq by a single thread; for the towers the element is
-    // first reduced to its norm:  a^-1 = conj(a) / N(a),  conj(a) = prod of the non-trivial Frobenius images.
+    // four slots distinct.  One inversion in Fq; for the towers the element is first reduced to its norm:
+    // a^-1 = conj(a) / N(a),  conj(a) = prod of the non-trivial Frobenius images.  On the device the Fq inversion is
+    // done by the whole warp (fq_inv_coop.cuh: limb i of lane 0's element on lane i), with the one-thread binary
+    // gcd of fq.cuh as the fallback; the host emulation runs the one-thread version.
     MSM_OP void inv_lane0(int d, int a, int t0, int t1) const {
-        if (DEG == 1) {
-            MSM_FOR_COMP(c) {
-                if (lane() == 0) { fq_t x, r; ld(x, a, c); fq_inv<M>(r, x); st(d, c, r); }
-            }
-#ifndef MNT753_HOST_EMU
-            __syncwarp();
-#endif
-            return;
+        int src = a, dst = d;
+        if (DEG > 1) {
+            frob(t0, a, 1);
+            if (DEG == 3) { frob(t1, a, 2); mul(t0, t0, t1); }
+            mul(t1, a, t0);                  // norm, lies in Fq: (N, 0[, 0])
+            src = dst = t1;
         }
-        frob(t0, a, 1);
-        if (DEG == 3) { frob(t1, a, 2); mul(t0, t0, t1); }
-        mul(t1, a, t0);                      // norm, lies in Fq: (N, 0[, 0])
 #ifdef MNT753_HOST_EMU
-        { fq_t x, r; ld(x, t1, 0); fq_inv<M>(r, x); st(t1, 0, r); }
+        { fq_t x, r; ld(x, src, 0); fq_inv<M>(r, x); st(dst, 0, r); }
 #else
-        if (comp == 0 && lane() == 0) { fq_t x, r; ld(x, t1, 0); fq_inv<M>(r, x); st(t1, 0, r); }
+        if (comp == 0) {
+            const int l = lane();
+            __syncwarp();
+            // word k of quad q of lane 0's coefficient 0: 32-bit index (q * LANES) * 4 + k from the column of lane 0
+            const int w = (l >> 2) * (LANES * 4) + (l & 3);
+            uint32_t x = l < NLIMB ? reinterpret_cast<const uint32_t *>(elem(src, 0) - l)[w] : 0u;
+            const bool ok = fq_inv_coop<M>(x);
+            __syncwarp();
+            if (ok) {
+                if (l < NLIMB) reinterpret_cast<uint32_t *>(elem(dst, 0) - l)[w] = x;
+            } else if (l == 0) {
+                fq_t y, r; ld(y, src, 0); fq_inv<M>(r, y); st(dst, 0, r);
+            }
+            __syncwarp();
+        }
 #endif
-        mul(d, t0, t1);
+        if (DEG > 1) mul(d, t0, t1);
     }
 
     // per-lane test, identical in every warp of the team

@@ -307,6 +307,17 @@ __global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_test_field(int op, 
         case 5: T.neg_if(2, 0, true); break;
         case 6: T.mul_by_a(2, 0); break;
         case 7: T.mul(0, 0, 1); T.copy(2, 0); break;
+        case 8:   // Team::inv_lane0 (the tile inversion of the batched-affine accumulation) on every lane's element in turn
+            for (int src = 0; src < 32; ++src) {
+                T.copy_lane(3, 0, src);
+                T.sync();
+                if (team_any(!T.is_zero(3))) {
+                    T.inv_lane0(4, 3, 5, 6);
+                    T.copy_lane(5, 4, 0);
+                } else T.set_zero(5);
+                T.copy(2, 5, (threadIdx.x & 31) == src);
+            }
+            break;
         default: T.dbl(2, 0); break;
     }
     T.sync();

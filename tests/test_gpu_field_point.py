@@ -50,6 +50,28 @@ def test_field_random(ctxs, oracle, curve, group):
 
 
 @pytest.mark.parametrize("curve,group", CG)
+def test_tile_inversion(ctxs, oracle, curve, group):
+    """Team::inv_lane0 on the device -- the warp-cooperative inversion of csrc/fq_inv_coop.cuh (Fq2 / Fq3 through the
+    norm) -- against the oracle's field inversion: edge values (1, 2, p - 1, powers of two, small and huge) and random."""
+    rng = np.random.default_rng(7 + curve * 10 + group)
+    p = po.fq_modulus(curve)
+    deg = po.degree(curve, group)
+    edge = [1, 2, 3, p - 1, p - 2, (p - 1) // 2, (p + 1) // 2, po.R % p, (1 << 752) % p, (1 << 32) - 1, 1 << 32, (1 << 64) + 1]
+    edge += [(1 << k) % p for k in range(1, 768, 37)]
+    vals = []
+    for e in edge:
+        vals += [e] + [0] * (deg - 1)                  # elements of the base field
+    for e in edge[:8]:
+        vals += [0] * (deg - 1) + [e]                  # pure top coefficient
+    n_rand = 700
+    vals += [int.from_bytes(rng.bytes(100), "little") % p for _ in range(n_rand * deg)]
+    a = po.ints_to_array(vals)
+    f = 0 if group == 1 else 1
+    got = ctxs[curve].selftest_field(group, 8, a)
+    assert (got == oracle.field_op(curve, f, 4, a)).all()
+
+
+@pytest.mark.parametrize("curve,group", CG)
 def test_point_ops(ctxs, oracle, golden, curve, group):
     z = golden["point_vectors"]
     key = "c%d_g%d" % (curve, group)
