@@ -208,11 +208,7 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 // passed on, the pair is marked idle), an odd one out is carried over, the piece's count is halved.
 // Returns the number of pairs listed (idle ones included).
 __device__ __forceinline__ uint32_t ba_plan(const BaView &v, uint32_t r, int lane, uint32_t &maxc) {
-#ifdef BA_DBG_VOLATILE_REFS
-    const volatile uint32_t *cur = v.refs[r & 1u];
-#else
     const uint32_t *cur = v.refs[r & 1u];
-#endif
     uint32_t *nxt = v.refs[(r + 1u) & 1u];
     uint32_t total = 0;
     for (uint32_t base = 0; base < v.npieces; base += 32u) {
@@ -282,10 +278,19 @@ __device__ __forceinline__ void prefetch_coord(const Team<F> &T, const uint32_t 
 #define BA_G2S_WAIT()
 #endif
 
-// The additions [p0, p0 + 32 B) of the share's pair list: forward pass, one inversion, backward pass.
-template <class F>
-__device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const BaView &v, uint32_t *nxt_refs, uint32_t p0, uint32_t B,
-                                        uint32_t P) {
+// Where a tile's additions come from: get(p) is addition p of the caller's list -- (source 0, source 1, scratch slot
+// of the sum, index of its reference in the output list) -- or an idle descriptor (x == REF_INF) beyond the list;
+// codes[p] parks the classification between the two passes.
+struct ListPairs {          // a share's planned pair list (k_batch_add)
+    const uint4 *pairs;
+    uint8_t *codes;
+    uint32_t P;
+    __device__ __forceinline__ uint4 get(uint32_t p) const { return p < P ? pairs[p] : make_uint4(REF_INF, REF_INF, 0u, 0u); }
+};
+
+// The additions [p0, p0 + 32 B) of the list: forward pass, one inversion, backward pass.
+template <class F, class Src>
+__device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const Src &src, uint32_t *nxt_refs, uint32_t p0, uint32_t B) {
     constexpr int DEG = F::DEG;
     constexpr int EW = DEG * NLIMB, AFFW = 2 * EW;
     const int lane = threadIdx.x & 31;
@@ -295,8 +300,8 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
     T.set_one(s.INV);
     // descriptors are read two steps ahead and the coordinates of the next step are pulled into L2, so
     // that neither the list nor the gathers are waited for at DRAM latency
-    uint4 nxt = (p0 + lane < P) ? v.pairs[p0 + lane] : idle;
-    uint4 nxt2 = (B > 1u && p0 + 32u + lane < P) ? v.pairs[p0 + 32u + lane] : idle;
+    uint4 nxt = src.get(p0 + lane);
+    uint4 nxt2 = B > 1u ? src.get(p0 + 32u + lane) : idle;
     for (uint32_t i = 0; i < B; ++i) {
         const uint32_t p = p0 + i * 32u + lane;
         const uint4 d = nxt;
@@ -307,7 +312,7 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
             prefetch_coord(T, ba_ref_ptr(a, nxt.x, AFFW));
             if (nxt.y != REF_INF) prefetch_coord(T, ba_ref_ptr(a, nxt.y, AFFW));
         }
-        nxt2 = (i + 2 < B && p + 64u < P) ? v.pairs[p + 64u] : idle;
+        nxt2 = i + 2 < B ? src.get(p + 64u) : idle;
         BA_G2S_BEGIN();
         BA_G2S(T, s.X1, g1, valid);
         BA_G2S(T, s.X2, g2, has2);
@@ -320,21 +325,17 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
             T.neg_if(s.Y1, s.Y1, (d.x & REF_NEG) != 0u, pred);
             T.neg_if(s.Y2, s.Y2, (d.y & REF_NEG) != 0u, pred);
         });
-        if (valid && T.comp == 0) v.codes[p] = (uint8_t)code;                      // parked until the backward pass
+        if (valid && T.comp == 0) src.codes[p] = (uint8_t)code;                    // parked until the backward pass
         BA_S2G(T, a.scratch + (size_t)d.z * AFFW, s.INV, valid);                    // exclusive prefix, parked in the output slot
         T.mul(s.INV, s.INV, s.X2);
     }
     // ---- one inversion for the whole tile
     tile_inverse(T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
-#ifdef BA_DBG_FENCE_TILE
-    __threadfence();
-    T.sync();
-#endif
     // ---- backward: the additions
     {
         const uint32_t pl = p0 + (B - 1u) * 32u + lane;
-        nxt = (pl < P) ? v.pairs[pl] : idle;
-        nxt2 = (B > 1u && pl - 32u < P) ? v.pairs[pl - 32u] : idle;
+        nxt = src.get(pl);
+        nxt2 = B > 1u ? src.get(pl - 32u) : idle;
     }
     for (int i = (int)B - 1; i >= 0; --i) {
         const uint32_t p = p0 + (uint32_t)i * 32u + lane;
@@ -349,8 +350,8 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
             if (nxt.y != REF_INF) { prefetch_coord(T, n2); prefetch_coord(T, n2 + EW); }
             prefetch_coord(T, a.scratch + (size_t)nxt.z * AFFW);
         }
-        nxt2 = (i > 1 && p - 64u < P) ? v.pairs[p - 64u] : idle;
-        const uint32_t code = valid ? v.codes[p] : (uint32_t)BA_IDLE;
+        nxt2 = i > 1 ? src.get(p - 64u) : idle;
+        const uint32_t code = valid ? src.codes[p] : (uint32_t)BA_IDLE;
         BA_G2S_BEGIN();
         BA_G2S(T, s.X1, g1, valid);
         BA_G2S(T, s.Y1, g1 + EW, valid);
@@ -397,7 +398,7 @@ __device__ __forceinline__ uint32_t ba_share(const Team<F> &T, const BaArgs &a, 
             const uint32_t left = (P - p0 + 31u) / 32u;
             uint32_t B = left;
             if (left > (uint32_t)BA_BMAX) B = left >= 2u * (uint32_t)BA_BMAX ? (uint32_t)BA_BMAX : (left + 1u) / 2u;
-            ba_tile(T, a, v, v.refs[(r + 1u) & 1u], p0, B, P);
+            ba_tile(T, a, ListPairs{v.pairs, v.codes, P}, v.refs[(r + 1u) & 1u], p0, B);
             p0 += 32u * B;
         }
     }

@@ -6,6 +6,13 @@
 
 namespace {
 
+#ifndef B200_TREE_AFFINE_MIN
+#define B200_TREE_AFFINE_MIN 100000
+#endif
+// additions in a reduction round from which batched-affine beats one Jacobian addition per lane, for Fq; the towers'
+// Jacobian additions are dearer in proportion (measured: profiles/r02_ab_tree_threshold.txt)
+constexpr uint64_t TREE_AFFINE_MIN = B200_TREE_AFFINE_MIN;
+
 // teams that take a share of an MSM with at most `emax` sorted entries: every team of the persistent grid, but no
 // share below 256 entries (eight additions per lane: below that a round is all fixed cost)
 template <class G>
@@ -31,14 +38,6 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     a.NB = 1u << (c - 1);
     a.K = (uint32_t)a.W * a.NB;
     const uint64_t emax = (uint64_t)n * a.Wd;
-    // bucket-reduce segment length: keep >= ~32k lanes of segments when there are that many buckets
-    // (one wave of k_bucket_reduce: its 12-slot teams fit 6 per SM for G1, fewer for the towers)
-    typedef TailCfg<G> TCp;
-    const uint64_t resident_lanes = (uint64_t)ctx->sm_count * std::max<size_t>(1, (size_t)(220 * 1024) / (TCp::TS::SMEM + 1024)) * TCp::TPB * 32;
-    uint32_t m = 1;
-    while ((uint64_t)a.K / m > resident_lanes && m * 2 <= a.NB && m < 256) m *= 2;
-    a.m = m;
-    a.nseg = a.NB / m;
     p.nscan = (a.K + SCAN_B - 1) / SCAN_B;
 
     size_t off = 0;
@@ -54,12 +53,27 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     // small regions, pair list and codes (share t starts at (E0 >> 1) + t)
     const uint32_t U = shares_for<G>(ctx, emax);
     const uint64_t capA = emax / 2 + 1, capB = (emax + a.K + U) / 4 + 2, capF = 2 * (uint64_t)U + 2;
+    // bucket-reduction tree (bucket_tree.cuh): a reference and a scratch slot per node, 2 NB nodes per set
+    TreeArgs &t = p.t;
+    memset(&t, 0, sizeof t);
+    t.W = (uint32_t)a.W;
+    t.NB = a.NB;
+    t.k = (uint32_t)(c - 1);
+    t.h = t.k > 5u ? t.k - 5u : 0u;
+    t.nodes = 2u * a.NB;
+    // affine rounds while a round has enough additions to pay for its tile inversion (bucket_tree.cuh)
+    t.hA = 0;
+    while (t.hA < t.h && (uint64_t)a.W * (a.NB >> (t.hA + 2)) * (3u + t.hA) * G::F::DEG >= TREE_AFFINE_MIN) ++t.hA;
+    t.jbase = t.hA < t.h ? a.NB - (a.NB >> t.hA) : t.nodes;
+    t.jnodes = t.nodes - t.jbase;
+    const uint64_t capT = (uint64_t)a.W * t.nodes;
+    p.slots = capA + capB + capF + capT;
     b.K = a.K;
     b.U = U;
     b.offs = a.offs;
     b.refs[0] = a.entries;
     b.refs[1] = (uint32_t *)take((size_t)emax * 4 + 4);
-    b.scratch = (uint32_t *)take((size_t)(capA + capB + capF) * AFFB);
+    b.scratch = (uint32_t *)take((size_t)p.slots * AFFB);
     b.capA = (uint32_t)capA;
     b.fx_scratch_base = (uint32_t)(capA + capB);
     b.pairs = (uint4 *)take((size_t)(emax / 2 + U + 1) * 16);
@@ -73,12 +87,12 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     b.fx_offs = (uint32_t *)take(((size_t)2 * U + 1) * 4);
     b.fx_cntv = (uint32_t *)take(((size_t)2 * U + 1) * 4);
     b.fx_bucket = (uint32_t *)take((size_t)2 * U * 4);
-    a.bucket_ref = b.bucket_ref;
-    a.ba_scratch = b.scratch;
-    a.segsum = (uint32_t *)take((size_t)a.W * a.nseg * JACB);
-    const size_t lvl = (size_t)a.W * ((a.nseg + 31) / 32) * JACB;
-    a.tmp_a = (uint32_t *)take(lvl);
-    a.tmp_b = (uint32_t *)take(lvl);
+    t.slot_base = (uint32_t)(capA + capB + capF);
+    t.bucket_ref = b.bucket_ref;
+    t.R = (uint32_t *)take((size_t)capT * 4);
+    t.codes = (uint8_t *)take((size_t)a.K);            // the largest round has 3 K / 4 additions
+    p.fin = (uint32_t *)take((size_t)a.W * (t.k + 1) * JACB);
+    t.J = (uint32_t *)take((size_t)a.W * t.jnodes * JACB);
     a.winsum = (uint32_t *)take((size_t)a.W * JACB);
     a.result = (uint32_t *)take(JACB);
     p.bytes = off;
@@ -100,7 +114,9 @@ int prepare_kernels(b200msm_ctx *ctx) {
     int rc;
     if ((rc = set_smem(ctx, k_batch_add<G>, BaCfg<G>::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_ba_fixup<G>, BaCfg<G>::TS::SMEM))) return rc;
-    if ((rc = set_smem(ctx, k_bucket_reduce<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_tree_round<G>, BaCfg<G>::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_tree_finish<G>, TC::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_tree_jac<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_sum<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_horner<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_to_affine<G>, TC::TS::SMEM))) return rc;
@@ -178,6 +194,8 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     int rc = prepare_kernels<G>(ctx);
     if (rc) return rc;
     Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
+    if (probe.slots >= (uint64_t(1) << 30))
+        return fail(ctx, B200MSM_ERR_ARG, "n = %zu with %d digits per scalar needs %llu scratch points (limit 2^30 per call); shard the MSM", n, cfg.Wd, (unsigned long long)probe.slots);
     if ((rc = grow_arena(ctx, ln, probe.bytes))) return rc;
     Plan p = make_plan<G>(ctx, n, cfg, ln.arena);
     MsmArgs &a = p.a;
@@ -235,25 +253,28 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     launches += 2;
     CU(cudaEventRecord(ln.ev[3], st));
 
-    const unsigned tail_lanes = TC::TPB * 32;
-    k_bucket_reduce<G><<<((unsigned)a.W * a.nseg + tail_lanes - 1) / tail_lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
-    launches += 1;
+    // bucket reduction (bucket_tree.cuh): h rounds of pairwise affine additions, then the k + 1 short lists of every set
     {
-        const uint32_t *in = a.segsum;
-        uint32_t nin = a.nseg;
-        uint32_t *bufs[2] = {a.tmp_a, a.tmp_b};
-        int flip = 0;
-        while (nin > 1) {
-            const uint32_t nout = (nin + 31) / 32;
-            uint32_t *out = nout == 1 ? a.winsum : bufs[flip];
-            k_sum<G><<<((unsigned)a.W * nout + TC::TPB - 1) / TC::TPB, TC::TS::THREADS, TC::TS::SMEM, st>>>(
-                in, out, (uint32_t)a.W, nin, 32u);
+        TreeArgs t = p.t;
+        for (uint32_t r = 1; r <= t.h; ++r) {
+            t.r = r;
+            t.q = t.NB >> (r + 1);
+            t.logq = t.k - (r + 1);
+            t.P = t.W * t.q * (2u + r);
+            if (r <= t.hA) {
+                const uint64_t teams = std::min<uint64_t>((uint64_t)ctx->sm_count * BC::TPB, ((uint64_t)t.P + 31) / 32);
+                const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count, teams);
+                k_tree_round<G><<<blocks, BC::TS::THREADS, BC::TS::SMEM, st>>>(b, t);
+            } else {
+                const unsigned lanes = TC::TPB * 32;
+                k_tree_jac<G><<<(t.P + lanes - 1) / lanes, TC::TS::THREADS, TC::TS::SMEM, st>>>(b, t);
+            }
             ++launches;
-            in = out;
-            nin = nout;
-            flip ^= 1;
         }
-        if (in != a.winsum) a.winsum = const_cast<uint32_t *>(in);  // nseg == 1: segment sums are the window sums
+        const unsigned lists = t.W * (t.k + 1u);
+        k_tree_finish<G><<<(lists + TC::TPB - 1) / TC::TPB, TC::TS::THREADS, TC::TS::SMEM, st>>>(b, t, p.fin);
+        k_sum<G><<<((unsigned)a.W + TC::TPB - 1) / TC::TPB, TC::TS::THREADS, TC::TS::SMEM, st>>>(p.fin, a.winsum, (uint32_t)a.W, t.k + 1u, 32u);
+        launches += 2;
     }
     k_horner<G><<<1, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
     ++launches;

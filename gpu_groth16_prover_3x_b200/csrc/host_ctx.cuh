@@ -13,6 +13,7 @@
 #include "../../include/b200_msm.h"
 #include "msm_kernels.cuh"
 #include "batch_affine.cuh"
+#include "bucket_tree.cuh"
 #include "util_kernels.cuh"
 
 using namespace mnt753;
@@ -148,6 +149,9 @@ inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bo
 struct Plan {
     MsmArgs a;
     BaArgs b;        // the batched-affine accumulation (batch_affine.cuh)
+    TreeArgs t;      // the bucket-reduction tree (bucket_tree.cuh)
+    uint32_t *fin;   // its k + 1 Jacobian terms per set
+    uint64_t slots;  // scratch points in all
     size_t bytes;
     uint32_t *bsum;
     uint32_t nscan;

@@ -8,8 +8,9 @@
 //   k_scatter         single-pass radix (counting) sort: point indices grouped by (window, bucket)
 //   k_batch_add       bucket accumulation (batch_affine.cuh): rounds of pairwise affine additions, one
 //   k_ba_fixup        persistent launch, every team takes its share of the sorted list through all rounds
-//   k_bucket_reduce   per (window, segment): running-sum reduction  sum_b b*B_b  of a bucket segment
-//   k_sum             plain segmented sums (segment sums -> window sums)
+//   k_tree_round      bucket reduction  sum_b (b + 1) B_b  as a tree of pairwise affine additions (bucket_tree.cuh):
+//   k_tree_finish     one launch per level, then the k + 1 short lists of every set
+//   k_sum             plain segmented sums (the terms of a set -> its window sum; partial results of shards)
 //   k_horner          window combine: result = sum_w 2^(c*w) * S_w
 //
 // Work decomposition: a TEAM = DEG warps handles 32 lanes (see fe.cuh); blocks hold TPB teams.
@@ -30,8 +31,6 @@ struct MsmArgs {
     uint32_t tab_stride;  // points per precomputed table (table t holds 2^(c*W*t) * P_i), see BaseSet
     uint32_t NB;       // buckets per set = 2^(c-1)
     uint32_t K;        // W * NB
-    uint32_t m;        // bucket-reduce segment length (power of two)
-    uint32_t nseg;     // NB / m
     // buffers
     const uint32_t *bases;      // affine AoS, 2*DEG*24 words per point; row t * tab_stride + i = 2^(c*W*t) * P_i
     const uint8_t *base_inf;    // 1 if base is infinity
@@ -40,14 +39,8 @@ struct MsmArgs {
     uint32_t *offs;             // K + 1
     uint32_t *cursor;           // K
     uint32_t *entries;          // n * Wd : table row | sign << 31
-    uint32_t *segsum;           // W * nseg Jacobian points
-    uint32_t *tmp_a, *tmp_b;    // scratch point arrays for k_sum levels
     uint32_t *winsum;           // W Jacobian points
     uint32_t *result;           // 1 Jacobian point
-    // what the batched-affine accumulation (batch_affine.cuh) leaves of every bucket: a reference to one affine
-    // point -- a table row (bit 31: negated), a slot of the scratch array (bit 30), or 0xffffffff for nothing
-    const uint32_t *bucket_ref;
-    const uint32_t *ba_scratch;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -300,63 +293,6 @@ struct TailCfg {
     static constexpr int TPB = DEG == 1 ? 2 : 1;
     typedef TeamSetup<G, NSLOT, TPB> TS;
 };
-
-// running-sum reduction of one bucket segment per lane; out[w*nseg + seg] = sum_{j<m} (seg*m+j+1) * B[w][seg*m+j].
-// A bucket is one affine point (or nothing), given by reference: see MsmArgs::bucket_ref.
-template <class G>
-__global__ void __launch_bounds__(TailCfg<G>::TS::THREADS) k_bucket_reduce(MsmArgs a) {
-    typedef typename G::F F;
-    typedef TailCfg<G> C;
-    constexpr int EW = F::DEG * NLIMB, AFFW = 2 * EW, JACW = 3 * EW;
-    extern __shared__ uint4 smem[];
-    __shared__ uint32_t s_flags[C::TPB][4];
-    int team;
-    const Team<F> T = C::TS::make(smem, s_flags, team);
-    const int lane = threadIdx.x & 31;
-    const PtSlots tot = {0, 1, 2, 6, 7, 8, 9, 10, 11};
-    const PtSlots run = {3, 4, 5, 6, 7, 8, 9, 10, 11};
-    const uint32_t id = (blockIdx.x * C::TPB + team) * 32 + lane;
-    const bool valid = id < (uint32_t)a.W * a.nseg;
-    const uint32_t w = valid ? id / a.nseg : 0u, seg = valid ? id % a.nseg : 0u;
-    T.set_zero(tot.Z1);
-    T.set_zero(run.Z1);
-    bool run_inf = true;
-    for (int j = (int)a.m - 1; j >= 0; --j) {
-        const uint32_t key = w * a.NB + seg * a.m + (uint32_t)j;
-        const uint32_t ref = valid ? a.bucket_ref[key] : 0xffffffffu;
-        const bool ne = ref != 0xffffffffu;
-        if (team_any(ne)) {
-            const uint32_t *src = ((ref & 0x40000000u) ? a.ba_scratch : a.bases) + (size_t)(ref & 0x3fffffffu) * AFFW;
-            g2s(T, run.X2, src, ne);
-            g2s(T, run.Y2, src + EW, ne);
-            T.sync();
-            Ec<F>::madd(T, run, (ref >> 31) != 0u, ne, run_inf);
-        }
-        if (team_any(!run_inf)) {
-            T.copy(tot.X2, run.X1); T.copy(tot.Y2, run.Y1); T.copy(tot.Z2, run.Z1);
-            Ec<F>::add(T, tot, !run_inf);
-        }
-    }
-    // out = tot + (seg*m) * run : park tot in global, reuse its slots for the scalar multiple
-    uint32_t *out = a.segsum + (size_t)id * JACW;
-    store_jac(T, out, tot.X1, tot.Y1, tot.Z1, valid);
-    T.set_zero(tot.Z1);
-    const uint32_t k = seg * a.m;
-    int top = 31 - __clz(max(a.NB, 2u) - 1u);  // highest possible bit of k
-    for (int bit = top; bit >= 0; --bit) {
-        Ec<F>::dbl(T, tot, true);
-        const bool on = valid && ((k >> bit) & 1u) && !run_inf;
-        if (team_any(on)) {
-            T.copy(tot.X2, run.X1); T.copy(tot.Y2, run.Y1); T.copy(tot.Z2, run.Z1);
-            Ec<F>::add(T, tot, on);
-        }
-    }
-    T.sync();
-    load_jac(T, tot.X2, tot.Y2, tot.Z2, out, valid);
-    T.set_zero(tot.Z2, !valid);
-    Ec<F>::add(T, tot, valid);
-    store_jac(T, out, tot.X1, tot.Y1, tot.Z1, valid);
-}
 
 // out[w*nout + o] = sum_{j<32} in[w*nin + o*32 + j]   (nout = ceil(nin/32)): one TEAM per output, one lane
 // per input, xor-butterfly of five full additions (every lane ends up with the sum; lane 0 stores it).
