@@ -107,12 +107,15 @@ int fail(b200msm_ctx *ctx, int code, const char *fmt, ...) {
 inline int degree_of(int curve, int group) { return group == B200MSM_G1 ? 1 : (curve == B200MSM_MNT4753 ? 2 : 3); }
 
 // ---- window-size / table choice ---------------------------------------------------------------
-// Time model in nanoseconds, calibrated on B200 (profiles/, tools/c_sweep.py): ~1.2 ns per batched-affine
-// addition (one per point and digit), ~10 ns per bucket in the running-sum reduction, ~0.3 ms of latency per
-// round of pairwise additions, and the serial window combine (c doublings per bucket set after the first).
-// The number of rounds is log2 of the LARGEST bucket: besides the average occupancy that is the top window,
-// which holds only rem = 754 - (Wd - 1) c bits and therefore piles n / 2^(rem-1) points on each of its few
-// buckets (c = 16: rem = 2, a quarter of all points in one bucket) -- widths with a short top window lose.
+// Time model in nanoseconds, calibrated on B200 (profiles/r02_size_sweep_1gpu.txt, tools/c_sweep.py): ~1.05 ns per
+// batched-affine addition (one per point and digit; x3 / x6 in the towers), ~0.15 ms of latency per round of the
+// accumulation (a tile inversion and two passes), and for the bucket reduction (bucket_tree.cuh) ~2.2 ns per bucket
+// in its affine rounds, ~0.11 ms per tree level, ~35 us per doubling of the final terms (c - 2 of them, serial) and
+// ~0.7 ms for the butterflies of the short lists and the window sum; bucket sets after the first cost c doublings each
+// in the window combine.  The number of accumulation rounds is log2 of the LARGEST bucket: besides the average
+// occupancy that is the top window, which holds only rem = 754 - (Wd - 1) c bits and therefore piles n / 2^(rem-1)
+// points on each of its few buckets (c = 16: rem = 2, a quarter of all points in one bucket) -- widths with a short
+// top window lose.
 struct TabCfg { int c, Wd, NT, G; };
 inline int digits_for(int c) { return (MNT753_NUM_BITS + 1 + c - 1) / c; }
 
@@ -139,8 +142,11 @@ inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bo
         const double top = rem >= c ? 0.0 : double(n) / double(1u << (rem > 1 ? rem - 1 : 0));
         double rounds = 1.0;
         for (double occ = avg + top; occ > 1.0; occ *= 0.5) rounds += 1.0;
-        const double cost = double(Wd) * double(n) * 1.2 * k + double(G) * NB * 10.0 * k + double(G - 1) * c * 40000.0 * deg +
-                            rounds * 300000.0 * (deg == 1 ? 1.0 : deg * 0.8) + double(G) * 60000.0 * deg;
+        const double lat = deg == 1 ? 1.0 : (deg == 2 ? 1.4 : 1.9);               // latency of one field operation in the towers
+        const double levels = c > 6 ? double(c - 6) : 0.0;
+        const double cost = double(Wd) * double(n) * 1.05 * k + rounds * 150000.0 * lat +
+                            double(G) * NB * 2.2 * k + (levels * 110000.0 + 700000.0 + double(c) * 35000.0) * lat +
+                            double(G - 1) * c * 35000.0 * lat;
         if (cost < best_cost) { best_cost = cost; best = {c, Wd, NT, G}; }
     }
     return best;
