@@ -6,6 +6,12 @@
 
 namespace {
 
+// a device allocation that is released on every return path
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+
 #ifndef B200_TREE_AFFINE_MIN
 #define B200_TREE_AFFINE_MIN 100000
 #endif
@@ -384,12 +390,13 @@ int run_test(b200msm_ctx *ctx, bool point, int op, size_t n, const uint64_t *a, 
     typedef TailCfg<G> TC;
     constexpr size_t EB = G::F::DEG * NLIMB * 4;
     const size_t ab = point ? 3 * EB : EB, bb = point ? (op == 0 ? 2 * EB : 3 * EB) : EB, ob = ab;
-    uint32_t *da = nullptr, *db = nullptr, *dout = nullptr, *dfl = nullptr;
-    CU(cudaMalloc(&da, n * ab));
-    CU(cudaMalloc(&dout, n * ob));
-    CU(cudaMemcpy(da, a, n * ab, cudaMemcpyHostToDevice));
-    if (b) { CU(cudaMalloc(&db, n * bb)); CU(cudaMemcpy(db, b, n * bb, cudaMemcpyHostToDevice)); }
-    if (flags) { CU(cudaMalloc(&dfl, n * 4)); CU(cudaMemcpy(dfl, flags, n * 4, cudaMemcpyHostToDevice)); }
+    DevBuf ba, bb2, bo, bf;
+    CU(cudaMalloc(&ba.p, n * ab));
+    CU(cudaMalloc(&bo.p, n * ob));
+    CU(cudaMemcpy(ba.p, a, n * ab, cudaMemcpyHostToDevice));
+    if (b) { CU(cudaMalloc(&bb2.p, n * bb)); CU(cudaMemcpy(bb2.p, b, n * bb, cudaMemcpyHostToDevice)); }
+    if (flags) { CU(cudaMalloc(&bf.p, n * 4)); CU(cudaMemcpy(bf.p, flags, n * 4, cudaMemcpyHostToDevice)); }
+    uint32_t *da = (uint32_t *)ba.p, *db = (uint32_t *)bb2.p, *dout = (uint32_t *)bo.p, *dfl = (uint32_t *)bf.p;
     const unsigned lanes = TC::TPB * 32, grid = (unsigned)((n + lanes - 1) / lanes);
     if (point) {
         CU(cudaFuncSetAttribute(k_test_point<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
@@ -401,31 +408,25 @@ int run_test(b200msm_ctx *ctx, bool point, int op, size_t n, const uint64_t *a, 
     CU(cudaGetLastError());
     CU(cudaDeviceSynchronize());
     CU(cudaMemcpy(out, dout, n * ob, cudaMemcpyDeviceToHost));
-    cudaFree(da); cudaFree(db); cudaFree(dout); cudaFree(dfl);
     return B200MSM_OK;
 }
 
-// sum of n Jacobian partial results (one per GPU shard) on the device -> one Jacobian point
+// sum of n Jacobian points (the partial results of the shards) -> one Jacobian point, all on the device and on
+// stream st: 32-ary butterfly levels (k_sum), then k_horner with one window for the (1, 1, 0) form of infinity.
+// scratch: 2 * (ceil(n / 32) + 1) Jacobian points.
 template <class G>
-int run_fold(b200msm_ctx *ctx, const uint64_t *xyz, size_t n, uint64_t *out) {
+int fold_dev(b200msm_ctx *ctx, cudaStream_t st, const uint32_t *din, size_t n, uint32_t *scratch, uint32_t *dres) {
     typedef TailCfg<G> TC;
-    constexpr size_t JACW = 3 * G::F::DEG * NLIMB, JACB = JACW * 4;
-    const size_t lvl = (n + 31) / 32 + 1;
-    uint32_t *din = nullptr, *buf[2] = {nullptr, nullptr}, *dres = nullptr;
-    CU(cudaMalloc(&din, (n ? n : 1) * JACB));
-    CU(cudaMalloc(&buf[0], lvl * JACB));
-    CU(cudaMalloc(&buf[1], lvl * JACB));
-    CU(cudaMalloc(&dres, JACB));
-    CU(cudaMemcpy(din, xyz, n * JACB, cudaMemcpyDefault));
-    CU(cudaFuncSetAttribute(k_sum<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
-    CU(cudaFuncSetAttribute(k_horner<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
-    const unsigned tail_lanes = TC::TPB * 32;
+    constexpr size_t JACW = 3 * G::F::DEG * NLIMB;
+    int rc = prepare_kernels<G>(ctx);
+    if (rc) return rc;
+    uint32_t *buf[2] = {scratch, scratch + ((n + 31) / 32 + 1) * JACW};
     const uint32_t *in = din;
     uint32_t nin = (uint32_t)n;
     int flip = 0;
     do {  // at least one pass so that the input is never aliased
         const uint32_t nout = (nin + 31) / 32;
-        k_sum<G><<<(nout + TC::TPB - 1) / TC::TPB, TC::TS::THREADS, TC::TS::SMEM>>>(in, buf[flip], 1u, nin, 32u);
+        k_sum<G><<<(nout + TC::TPB - 1) / TC::TPB, TC::TS::THREADS, TC::TS::SMEM, st>>>(in, buf[flip], 1u, nin, 32u);
         in = buf[flip];
         nin = nout;
         flip ^= 1;
@@ -436,34 +437,59 @@ int run_fold(b200msm_ctx *ctx, const uint64_t *xyz, size_t n, uint64_t *out) {
     a.c = 1;
     a.winsum = const_cast<uint32_t *>(in);
     a.result = dres;
-    k_horner<G><<<1, TC::TS::THREADS, TC::TS::SMEM>>>(a);
+    k_horner<G><<<1, TC::TS::THREADS, TC::TS::SMEM, st>>>(a);
     CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out, dres, JACB, cudaMemcpyDeviceToHost));
-    cudaFree(din); cudaFree(buf[0]); cudaFree(buf[1]); cudaFree(dres);
+    return B200MSM_OK;
+}
+
+template <class G>
+int to_affine_dev(b200msm_ctx *ctx, cudaStream_t st, size_t n, const uint32_t *din, uint32_t *dout) {
+    typedef TailCfg<G> TC;
+    int rc = prepare_kernels<G>(ctx);
+    if (rc) return rc;
+    const unsigned lanes = TC::TPB * 32;
+    k_to_affine<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM, st>>>((uint32_t)n, din, dout);
+    CU(cudaGetLastError());
+    return B200MSM_OK;
+}
+
+// host-facing: points in from host or device memory, result to the host, through the context's tail buffers
+template <class G>
+int run_fold(b200msm_ctx *ctx, const uint64_t *xyz, size_t n, uint64_t *out) {
+    constexpr size_t JACW = 3 * G::F::DEG * NLIMB, JACB = JACW * 4;
+    int rc = tail_reserve(ctx, (n + fold_scratch_points(n) + 1) * JACB, JACB);
+    if (rc) return rc;
+    TailBuf &t = ctx->tail;
+    uint32_t *din = (uint32_t *)t.d, *scratch = din + n * JACW, *dres = scratch + fold_scratch_points(n) * JACW;
+    CU(cudaMemcpyAsync(din, xyz, n * JACB, cudaMemcpyDefault, t.st));
+    if ((rc = fold_dev<G>(ctx, t.st, din, n, scratch, dres))) return rc;
+    CU(cudaMemcpyAsync(t.h, dres, JACB, cudaMemcpyDeviceToHost, t.st));
+    CU(cudaStreamSynchronize(t.st));
+    memcpy(out, t.h, JACB);
     return B200MSM_OK;
 }
 
 // ---- affine normalisation / synthetic bases ---------------------------------------------------
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-};
-
 template <class G>
 int run_to_affine(b200msm_ctx *ctx, size_t n, const uint64_t *xyz, uint64_t *out) {
-    typedef TailCfg<G> TC;
     constexpr size_t EB = G::F::DEG * NLIMB * 4;
-    DevBuf in, o;
-    CU(cudaMalloc(&in.p, n * 3 * EB));
-    CU(cudaMalloc(&o.p, n * 2 * EB));
-    CU(cudaMemcpy(in.p, xyz, n * 3 * EB, cudaMemcpyDefault));
-    CU(cudaFuncSetAttribute(k_to_affine<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
-    const unsigned lanes = TC::TPB * 32;
-    k_to_affine<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, (const uint32_t *)in.p, (uint32_t *)o.p);
-    CU(cudaGetLastError());
-    CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(out, o.p, n * 2 * EB, cudaMemcpyDefault));
+    int rc = tail_reserve(ctx, n * 5 * EB, n * 2 * EB);
+    if (rc) return rc;
+    TailBuf &t = ctx->tail;
+    uint32_t *din = (uint32_t *)t.d, *dout = din + n * 3 * (EB / 4);
+    CU(cudaMemcpyAsync(din, xyz, n * 3 * EB, cudaMemcpyDefault, t.st));
+    if ((rc = to_affine_dev<G>(ctx, t.st, n, din, dout))) return rc;
+    cudaPointerAttributes pattr;
+    const bool out_on_device = cudaPointerGetAttributes(&pattr, out) == cudaSuccess && pattr.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    if (out_on_device) {
+        CU(cudaMemcpyAsync(out, dout, n * 2 * EB, cudaMemcpyDeviceToDevice, t.st));
+        CU(cudaStreamSynchronize(t.st));
+    } else {
+        CU(cudaMemcpyAsync(t.h, dout, n * 2 * EB, cudaMemcpyDeviceToHost, t.st));
+        CU(cudaStreamSynchronize(t.st));
+        memcpy(out, t.h, n * 2 * EB);
+    }
     return B200MSM_OK;
 }
 
@@ -612,5 +638,5 @@ int run_teammul_bench(b200msm_ctx *ctx, int blocks_per_sm, int iters, double *go
 
 template <class G>
 constexpr GroupOps make_group_ops() {
-    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &run_synthetic<G>, &build_tables<G>, &run_teammul_bench<G>, &run_scalar_mul<G>, &reserve_lane<G>};
+    return GroupOps{&enqueue_msm<G>, &run_test<G>, &run_fold<G>, &run_to_affine<G>, &fold_dev<G>, &to_affine_dev<G>, &run_synthetic<G>, &build_tables<G>, &run_teammul_bench<G>, &run_scalar_mul<G>, &reserve_lane<G>};
 }

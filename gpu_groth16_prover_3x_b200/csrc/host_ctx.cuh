@@ -71,6 +71,15 @@ struct FftState {
     float last_ms = 0.f, tables_ms = 0.f;
 };
 
+// Scratch of the small host-facing routines (fold of partial points, affine normalisation, proof assembly): one
+// device buffer, one pinned host buffer and one stream per context, grown on demand and kept -- no allocation, no
+// device-wide synchronisation on the per-proof path.
+struct TailBuf {
+    cudaStream_t st = nullptr;
+    char *d = nullptr, *h = nullptr;
+    size_t dbytes = 0, hbytes = 0;
+};
+
 struct b200msm_ctx {
     int curve = 0;
     int device = 0;
@@ -81,6 +90,7 @@ struct b200msm_ctx {
     std::vector<BaseSet> sets;
     Lane lanes[NLANES];
     FftState fft;
+    TailBuf tail;
     std::string err = "";
 };
 
@@ -152,6 +162,32 @@ inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bo
     return best;
 }
 
+// make the context's tail buffers at least this large (contents are not preserved)
+inline int tail_reserve(b200msm_ctx *ctx, size_t dbytes, size_t hbytes) {
+    TailBuf &t = ctx->tail;
+    if (!t.st) CU(cudaStreamCreateWithFlags(&t.st, cudaStreamNonBlocking));
+    if (dbytes > t.dbytes) {
+        CU(cudaStreamSynchronize(t.st));
+        if (t.d) CU(cudaFree(t.d));
+        t.d = nullptr; t.dbytes = 0;
+        const size_t want = std::max<size_t>(dbytes + dbytes / 4, size_t(1) << 20);
+        CU(cudaMalloc(&t.d, want));
+        t.dbytes = want;
+    }
+    if (hbytes > t.hbytes) {
+        CU(cudaStreamSynchronize(t.st));
+        if (t.h) CU(cudaFreeHost(t.h));
+        t.h = nullptr; t.hbytes = 0;
+        const size_t want = std::max<size_t>(hbytes + hbytes / 4, size_t(1) << 16);
+        CU(cudaMallocHost(&t.h, want));
+        t.hbytes = want;
+    }
+    return B200MSM_OK;
+}
+
+// scratch points of GroupOps::fold_dev for n inputs
+inline size_t fold_scratch_points(size_t n) { return 2 * ((n + 31) / 32 + 1); }
+
 struct Plan {
     MsmArgs a;
     BaArgs b;        // the batched-affine accumulation (batch_affine.cuh)
@@ -173,6 +209,9 @@ struct GroupOps {
     int (*selftest)(b200msm_ctx *, bool, int, size_t, const uint64_t *, const uint64_t *, const uint32_t *, uint64_t *);
     int (*fold)(b200msm_ctx *, const uint64_t *, size_t, uint64_t *);
     int (*to_affine)(b200msm_ctx *, size_t, const uint64_t *, uint64_t *);
+    // device-side pieces of the two (no copies, no synchronisation): din n Jacobian points -> dres one; scratch of fold_scratch(n) bytes
+    int (*fold_dev)(b200msm_ctx *, cudaStream_t, const uint32_t *, size_t, uint32_t *, uint32_t *);
+    int (*to_affine_dev)(b200msm_ctx *, cudaStream_t, size_t, const uint32_t *, uint32_t *);
     int (*synthetic)(b200msm_ctx *, size_t, const uint64_t *, const uint64_t *, BaseSet &);
     int (*build_tables)(b200msm_ctx *, BaseSet &);
     int (*teammul_bench)(b200msm_ctx *, int, int, double *);

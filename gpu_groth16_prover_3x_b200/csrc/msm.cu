@@ -160,6 +160,9 @@ __global__ void __launch_bounds__(32) k_mb_inv(uint32_t *out, int iters) {
 
 }  // namespace
 
+// the per-group routines, for the proof assembly in prover.cu
+const GroupOps &b200msm_internal_ops(int curve, int group) { return ops_for(curve, group); }
+
 // ================================================================================================
 extern "C" {
 
@@ -208,6 +211,9 @@ void b200msm_destroy(b200msm_ctx *ctx) {
         if (ln.own_stream) cudaStreamDestroy(ln.own_stream);
     }
     for (auto &s : ctx->sets) if (s.used) { cudaFree(s.pts); cudaFree(s.inf); }
+    if (ctx->tail.st) { cudaStreamSynchronize(ctx->tail.st); cudaStreamDestroy(ctx->tail.st); }
+    if (ctx->tail.d) cudaFree(ctx->tail.d);
+    if (ctx->tail.h) cudaFreeHost(ctx->tail.h);
     delete ctx;
 }
 

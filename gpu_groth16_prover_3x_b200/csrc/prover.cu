@@ -27,6 +27,7 @@ struct b200msm_key {
 int b200msm_internal_fr_scale(b200msm_ctx *ctx, size_t n, const uint32_t *in_dev, const uint32_t *k_dev, uint32_t *out_dev, cudaStream_t st);
 extern "C" int b200msm_internal_reserve(b200msm_ctx *ctx, int lane, int slot, size_t n);
 int b200msm_internal_fft_prepare(b200msm_ctx *ctx, size_t d);
+const GroupOps &b200msm_internal_ops(int curve, int group);
 
 namespace {
 inline int g2_deg(const b200msm_ctx *ctx) { return ctx->curve == B200MSM_MNT4753 ? 2 : 3; }
@@ -192,26 +193,39 @@ int prove_finish(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int n, cons
     for (int g = 0; g < n; ++g)
         for (int l = 0; l < 4; ++l) { const int rcw = b200msm_wait(ctxs[g], l); if (!rc) rc = rcw; }
     if (rc) return rc;
-    // fold the shards' partial points; C = Ht + Lt + r * Bt1  (:198-200) is one fold over all of its 3 n terms
-    std::vector<uint64_t> buf((size_t)3 * n * 36 + (size_t)n * 108);
-    uint64_t A[36], B2[108], C[36];
-    for (int g = 0; g < n; ++g) memcpy(buf.data() + (size_t)g * 36, P[g].A, 288);
-    if ((rc = b200msm_fold(c0, B200MSM_G1, buf.data(), (size_t)n, A))) return rc;
-    for (int g = 0; g < n; ++g) memcpy(buf.data() + (size_t)g * 36 * dg, P[g].B2, (size_t)288 * dg);
-    if ((rc = b200msm_fold(c0, B200MSM_G2, buf.data(), (size_t)n, B2))) return rc;
+    // Fold the shards' partial points and normalise, all on shard 0's GPU: A = sum A_g, B = sum B2_g,
+    // C = sum (H_g + L_g + r Bt1_g)  (:198-200) -- one upload of the 5 n partial points, three folds and three affine
+    // normalisations chained on the context's tail stream, one download of the proof bytes (A || B || C).
+    const size_t J1 = 72, J2 = 72 * (size_t)dg, A1 = 48, A2 = 48 * (size_t)dg;      // 32-bit words of a Jacobian / affine point
+    const size_t in_words = (size_t)n * J1 + (size_t)n * J2 + (size_t)3 * n * J1;
+    const size_t sc_words = fold_scratch_points((size_t)3 * n) * J2;               // scratch of the largest fold, in the larger point size
+    const size_t out_words = 2 * A1 + A2;
+    if ((rc = tail_reserve(c0, (in_words + sc_words + 2 * J1 + J2 + out_words) * 4, std::max(in_words, out_words) * 4))) return rc;
+    b200msm_ctx *ctx = c0;      // for CU()
+    TailBuf &t = c0->tail;
+    uint32_t *h = reinterpret_cast<uint32_t *>(t.h);
+    uint32_t *hA = h, *hB = hA + (size_t)n * J1, *hC = hB + (size_t)n * J2;
     for (int g = 0; g < n; ++g) {
-        memcpy(buf.data() + (size_t)(3 * g) * 36, P[g].H, 288);
-        memcpy(buf.data() + (size_t)(3 * g + 1) * 36, P[g].L, 288);
-        memcpy(buf.data() + (size_t)(3 * g + 2) * 36, P[g].rB1, 288);
+        memcpy(hA + (size_t)g * J1, P[g].A, J1 * 4);
+        memcpy(hB + (size_t)g * J2, P[g].B2, J2 * 4);
+        memcpy(hC + (size_t)(3 * g) * J1, P[g].H, J1 * 4);
+        memcpy(hC + (size_t)(3 * g + 1) * J1, P[g].L, J1 * 4);
+        memcpy(hC + (size_t)(3 * g + 2) * J1, P[g].rB1, J1 * 4);
     }
-    if ((rc = b200msm_fold(c0, B200MSM_G1, buf.data(), (size_t)3 * n, C))) return rc;
-    uint64_t a_aff[24], b_aff[72], c_aff[24];
-    if ((rc = b200msm_to_affine(c0, B200MSM_G1, 1, A, a_aff))) return rc;
-    if ((rc = b200msm_to_affine(c0, B200MSM_G2, 1, B2, b_aff))) return rc;
-    if ((rc = b200msm_to_affine(c0, B200MSM_G1, 1, C, c_aff))) return rc;
-    memcpy(proof, a_aff, 192);
-    memcpy(proof + 192, b_aff, (size_t)192 * dg);
-    memcpy(proof + 192 + 192 * dg, c_aff, 192);
+    uint32_t *dA = reinterpret_cast<uint32_t *>(t.d), *dB = dA + (size_t)n * J1, *dC = dB + (size_t)n * J2, *dsc = dC + (size_t)3 * n * J1;
+    uint32_t *rA = dsc + sc_words, *rB = rA + J1, *rC = rB + J2, *dout = rC + J1;
+    CU(cudaSetDevice(c0->device));
+    CU(cudaMemcpyAsync(dA, h, in_words * 4, cudaMemcpyHostToDevice, t.st));
+    const GroupOps &g1 = b200msm_internal_ops(c0->curve, B200MSM_G1), &g2 = b200msm_internal_ops(c0->curve, B200MSM_G2);
+    if ((rc = g1.fold_dev(c0, t.st, dA, (size_t)n, dsc, rA))) return rc;
+    if ((rc = g1.to_affine_dev(c0, t.st, 1, rA, dout))) return rc;
+    if ((rc = g2.fold_dev(c0, t.st, dB, (size_t)n, dsc, rB))) return rc;
+    if ((rc = g2.to_affine_dev(c0, t.st, 1, rB, dout + A1))) return rc;
+    if ((rc = g1.fold_dev(c0, t.st, dC, (size_t)3 * n, dsc, rC))) return rc;
+    if ((rc = g1.to_affine_dev(c0, t.st, 1, rC, dout + A1 + A2))) return rc;
+    CU(cudaMemcpyAsync(h, dout, out_words * 4, cudaMemcpyDeviceToHost, t.st));
+    CU(cudaStreamSynchronize(t.st));
+    memcpy(proof, h, out_words * 4);
     return B200MSM_OK;
 }
 
