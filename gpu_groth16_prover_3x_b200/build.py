@@ -70,7 +70,7 @@ def build(force=False, verbose=False, extra_flags=None, out=None):
         # the command-line prover: plain C++ over the C ABI (no CUDA headers, no libff)
         cxx = HOST_CXX if os.path.exists(HOST_CXX) else "g++"
         subprocess.run([cxx, "-O2", "-std=c++17", "-o", os.path.join(HERE, "b200_prove"), os.path.join(CSRC, "prove_main.cpp"),
-                        "-L" + HERE, "-lb200msm", "-Wl,-rpath,$ORIGIN"], check=True)
+                        "-L" + HERE, "-lb200msm", "-lpthread", "-Wl,-rpath,$ORIGIN"], check=True)
     return LIB
 
 

@@ -268,6 +268,10 @@ struct Team {
             } else st(d, c, x);
         }
     }
+    // d = k * a for k in Fq (Montgomery form, in registers): the caller's own coefficient only
+    MSM_OP void scale_fq(int d, int a, const fq_t &k) const {
+        MSM_FOR_COMP(c) { fq_t x, y; ld(x, a, c); fq_mul<M>(y, x, k); st(d, c, y); }
+    }
     // d = 1 / a on EVERY lane (a != 0): the lanes run the binary gcd side by side (divergent, but the
     // alternative -- Fermat's a^(q-2), 750 squarings through the multiplier -- costs ten times more).  Used by
     // the affine normalisations (util_kernels.cuh), one inversion per lane and run of points.

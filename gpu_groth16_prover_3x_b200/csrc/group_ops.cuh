@@ -40,6 +40,8 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     a.n = (uint32_t)n;
     a.c = c;
     a.Wd = cfg.Wd;
+    a.glv = cfg.glv ? 1 : 0;
+    a.Wh = cfg.Wd / 2;
     a.W = cfg.G;
     a.NB = 1u << (c - 1);
     a.K = (uint32_t)a.W * a.NB;
@@ -130,6 +132,7 @@ int prepare_kernels(b200msm_ctx *ctx) {
     if ((rc = set_smem(ctx, k_synth_bases<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_batch_normalise<G>, TC::TS::SMEM))) return rc;
     if ((rc = set_smem(ctx, k_dbl_many<G>, DblCfg<G>::TS::SMEM))) return rc;
+    if ((rc = set_smem(ctx, k_psi_many<G>, TC::TS::SMEM))) return rc;
     done = true;
     return B200MSM_OK;
 }
@@ -149,7 +152,7 @@ int grow_arena(b200msm_ctx *ctx, Lane &ln, size_t bytes) {
 template <class G>
 TabCfg cfg_for(const b200msm_ctx *ctx, const BaseSet &bs, size_t n) {
     // window tables are used when they exist and the caller did not force a different window width
-    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) return TabCfg{bs.c_tab, digits_for(bs.c_tab), bs.NT, bs.G};
+    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) return TabCfg{bs.c_tab, bs.Wd, bs.NT, bs.G, bs.glv};
     return choose_cfg(n, G::F::DEG, ctx->c_override, 0, false);
 }
 
@@ -235,6 +238,7 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
             CU(cudaEventRecord(ln.ev[1], st));
         }
         k_from_mont<typename G::Fr><<<(unsigned)((hi - lo + 127) / 128), 128, 0, st>>>(a.scalars + lo * NLIMB, (uint32_t)(hi - lo));
+        if (a.glv) { k_glv_split<G::CURVE><<<(unsigned)((hi - lo + 127) / 128), 128, 0, st>>>(a.scalars + lo * NLIMB, (uint32_t)(hi - lo)); ++launches; }
         a.i0 = (uint32_t)lo;
         a.i1 = (uint32_t)hi;
         k_count<<<(unsigned)((hi - lo + 255) / 256), 256, 0, st>>>(a);
@@ -521,12 +525,20 @@ int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
     const unsigned lanes = TC::TPB * 32;
     const size_t runs = (n + B - 1) / B;
     const size_t tabw = n * 2 * (EB / 4);
-    for (int t = 1; t < bs.NT; ++t) {
+    // with split scalars (glv.cuh) only the lower half of the tables is built by doubling; table NT/2 + t = psi(table t)
+    const int by_doubling = bs.glv ? bs.NT / 2 : bs.NT;
+    for (int t = 1; t < by_doubling; ++t) {
         const unsigned dl = DblCfg<G>::TPB * 32;
         k_dbl_many<G><<<(unsigned)((n + dl - 1) / dl), DblCfg<G>::TS::THREADS, DblCfg<G>::TS::SMEM>>>((uint32_t)n, bs.c_tab * bs.G, bs.pts + (t - 1) * tabw,
                                                                                                     (uint32_t *)jac.p);
         k_batch_normalise<G><<<(unsigned)((runs + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>(
             (uint32_t)n, B, (const uint32_t *)jac.p, (uint32_t *)pre.p, bs.pts + t * tabw);
+    }
+    if (bs.glv) {
+        int rc = prepare_kernels<G>(ctx);
+        if (rc) return rc;
+        for (int t = by_doubling; t < bs.NT; ++t)
+            k_psi_many<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, bs.pts + (size_t)(t - by_doubling) * tabw, bs.pts + (size_t)t * tabw);
     }
     CU(cudaEventRecord(e1, 0));
     CU(cudaGetLastError());

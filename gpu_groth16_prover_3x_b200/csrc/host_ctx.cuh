@@ -14,6 +14,7 @@
 #include "msm_kernels.cuh"
 #include "batch_affine.cuh"
 #include "bucket_tree.cuh"
+#include "glv.cuh"
 #include "util_kernels.cuh"
 
 using namespace mnt753;
@@ -38,6 +39,8 @@ struct BaseSet {
     int c_tab = 0;  // window bits the tables were built for (0: no tables, any c allowed)
     int NT = 1;     // number of tables
     int G = 0;      // bucket sets when the tables are used
+    int Wd = 0;     // digits per scalar when the tables are used
+    bool glv = false;  // G2: scalars are split k = k0 + k1 lam, tables NT/2 .. NT-1 are psi of tables 0 .. NT/2-1 (glv.cuh)
     float build_ms = 0.f;
 };
 
@@ -126,30 +129,47 @@ inline int degree_of(int curve, int group) { return group == B200MSM_G1 ? 1 : (c
 // occupancy that is the top window, which holds only rem = 754 - (Wd - 1) c bits and therefore piles n / 2^(rem-1)
 // points on each of its few buckets (c = 16: rem = 2, a quarter of all points in one bucket) -- widths with a short
 // top window lose.
-struct TabCfg { int c, Wd, NT, G; };
+struct TabCfg { int c, Wd, NT, G; bool glv; };
 inline int digits_for(int c) { return (MNT753_NUM_BITS + 1 + c - 1) / c; }
+inline int half_digits_for(int c) { return (MNT753_GLV_HALF_BITS + 1 + c - 1) / c; }   // of one half of a split G2 scalar
 
 inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bool tables) {
     const double k = deg == 1 ? 1.0 : (deg == 2 ? 3.0 : 6.0);
     const size_t affb = (size_t)2 * deg * NLIMB * 4;
-    TabCfg best = {2, digits_for(2), 1, digits_for(2)};
+    TabCfg best = {2, digits_for(2), 1, digits_for(2), false};
     double best_cost = 1e300;
     for (int c = (c_fixed ? c_fixed : 2); c <= (c_fixed ? c_fixed : 22); ++c) {
-        const int Wd = digits_for(c);
+        int Wd = digits_for(c);
         size_t nt = 1;
         if (tables && n >= 256 && budget_bytes) {
             nt = budget_bytes / (n * affb);
             const size_t idx_cap = ((size_t(1) << 31) - 1) / n;
             if (nt > idx_cap) nt = idx_cap;
-            if (nt > (size_t)Wd) nt = Wd;
             if (nt < 1) nt = 1;
         }
-        const int G = (Wd + (int)nt - 1) / (int)nt;
-        const int NT = (Wd + G - 1) / G;
+        // G2 with at least two tables: split scalars (glv.cuh) -- two halves of Wh digits, Wh a multiple of the
+        // number of bucket sets so that a table belongs to one half
+        bool glv = false;
+        int G, NT, rem;
+        if (deg > 1 && nt >= 2) {
+            int Wh = half_digits_for(c);
+            if (nt > (size_t)(2 * Wh)) nt = 2 * Wh;
+            nt &= ~size_t(1);                                                      // the two halves have the same number of tables
+            G = (2 * Wh + (int)nt - 1) / (int)nt;
+            Wh = (Wh + G - 1) / G * G;
+            Wd = 2 * Wh;
+            NT = Wd / G;
+            glv = true;
+            rem = MNT753_GLV_HALF_BITS + 1 - (Wh - 1) * c;                        // bits of a half's top window (<= 0: it stays empty)
+        } else {
+            if (nt > (size_t)Wd) nt = Wd;
+            G = (Wd + (int)nt - 1) / (int)nt;
+            NT = (Wd + G - 1) / G;
+            rem = MNT753_NUM_BITS + 1 - (Wd - 1) * c;                             // bits of the top window
+        }
         const double NB = double(1u << (c - 1));
-        const int rem = MNT753_NUM_BITS + 1 - (Wd - 1) * c;                       // bits of the top window
         const double avg = double(n) * NT / NB;                                     // digits per bucket of a set
-        const double top = rem >= c ? 0.0 : double(n) / double(1u << (rem > 1 ? rem - 1 : 0));
+        const double top = (rem >= c || rem <= 0) ? 0.0 : double(n) / double(1u << (rem > 1 ? rem - 1 : 0));
         double rounds = 1.0;
         for (double occ = avg + top; occ > 1.0; occ *= 0.5) rounds += 1.0;
         const double lat = deg == 1 ? 1.0 : (deg == 2 ? 1.4 : 1.9);               // latency of one field operation in the towers
@@ -157,7 +177,7 @@ inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bo
         const double cost = double(Wd) * double(n) * 1.05 * k + rounds * 150000.0 * lat +
                             double(G) * NB * 2.2 * k + (levels * 110000.0 + 700000.0 + double(c) * 35000.0) * lat +
                             double(G - 1) * c * 35000.0 * lat;
-        if (cost < best_cost) { best_cost = cost; best = {c, Wd, NT, G}; }
+        if (cost < best_cost) { best_cost = cost; best = {c, Wd, NT, G, glv}; }
     }
     return best;
 }

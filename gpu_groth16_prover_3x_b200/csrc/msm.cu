@@ -39,7 +39,7 @@ int alloc_base_set(b200msm_ctx *ctx, int group, size_t n, bool tables, BaseSet &
     bs.group = group;
     bs.n = n;
     const TabCfg cfg = choose_cfg(n ? n : 1, deg, ctx->c_override, ctx->table_budget, tables);
-    if (cfg.NT > 1) { bs.c_tab = cfg.c; bs.NT = cfg.NT; bs.G = cfg.G; }
+    if (cfg.NT > 1) { bs.c_tab = cfg.c; bs.NT = cfg.NT; bs.G = cfg.G; bs.Wd = cfg.Wd; bs.glv = cfg.glv; }
     const size_t bytes = (size_t)bs.NT * n * 2 * deg * NLIMB * 4;
     CU(cudaMalloc(&bs.pts, bytes ? bytes : 256));
     cudaError_t e = cudaMalloc(&bs.inf, n ? n : 256);

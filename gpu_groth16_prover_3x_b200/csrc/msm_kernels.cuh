@@ -29,6 +29,8 @@ struct MsmArgs {
     int Wd;            // number of signed digits (windows) per scalar = ceil(754 / c)
     int W;             // number of bucket sets = ceil(Wd / NT): digit w lands in set w % W, using table w / W
     uint32_t tab_stride;  // points per precomputed table (table t holds 2^(c*W*t) * P_i), see BaseSet
+    int glv;           // G2 with window tables: the scalar is split k = k0 + k1 lam (glv.cuh), two halves of Wh digits each;
+    int Wh;            //   digit w of half h is digit h * Wh + w of the MSM, Wd = 2 Wh
     uint32_t NB;       // buckets per set = 2^(c-1)
     uint32_t K;        // W * NB
     // buffers
@@ -186,13 +188,13 @@ __global__ void __launch_bounds__(128) k_from_mont(uint32_t *scalars, uint32_t n
 // [-2^(c-1)+1, 2^(c-1)], a borrow of 2^c carried into the next window; W*c >= 754 so the top
 // window never overflows.  f(w, digit) is called for non-zero digits only.
 template <class Fn>
-__device__ __forceinline__ void for_each_digit(const uint32_t *k, int c, int W, Fn f) {
+__device__ __forceinline__ void for_each_digit(const uint32_t *k, int nl, int c, int W, Fn f) {
     uint32_t carry = 0;
     const uint32_t mask = (1u << c) - 1u, half = 1u << (c - 1);
     for (int w = 0; w < W; ++w) {
         const int o = w * c, word = o >> 5, sh = o & 31;
-        uint64_t v = k[word];
-        if (word + 1 < NLIMB) v |= (uint64_t)k[word + 1] << 32;
+        uint64_t v = word < nl ? k[word] : 0u;
+        if (word + 1 < nl) v |= (uint64_t)k[word + 1] << 32;
         uint32_t raw = ((uint32_t)(v >> sh) & mask) + carry;
         int d;
         if (raw > half) { d = (int)raw - (int)(1u << c); carry = 1; } else { d = (int)raw; carry = 0; }
@@ -200,13 +202,26 @@ __device__ __forceinline__ void for_each_digit(const uint32_t *k, int c, int W, 
     }
 }
 
-static __global__ void k_count(MsmArgs a) {
-    uint32_t i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.i1 || a.base_inf[i]) return;
+// every non-zero signed digit of scalar i: f(digit index, digit).  A split scalar (a.glv) is two half scalars of
+// 12 limbs with their signs in bit 31 of the top limb.
+template <class Fn>
+__device__ __forceinline__ void scalar_digits(const MsmArgs &a, uint32_t i, Fn f) {
     uint32_t k[NLIMB];
     const uint4 *p = reinterpret_cast<const uint4 *>(a.scalars + (size_t)i * NLIMB);
     for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w; }
-    for_each_digit(k, a.c, a.Wd, [&](int w, int d) {
+    if (!a.glv) { for_each_digit(k, NLIMB, a.c, a.Wd, f); return; }
+    for (int h = 0; h < 2; ++h) {
+        uint32_t *kh = k + 12 * h;
+        const bool neg = (kh[11] >> 31) != 0u;
+        kh[11] &= 0x7fffffffu;
+        for_each_digit(kh, 12, a.c, a.Wh, [&](int w, int d) { f(h * a.Wh + w, neg ? -d : d); });
+    }
+}
+
+static __global__ void k_count(MsmArgs a) {
+    uint32_t i = a.i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.i1 || a.base_inf[i]) return;
+    scalar_digits(a, i, [&](int w, int d) {
         uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
         atomicAdd(&a.count[(uint32_t)(w % a.W) * a.NB + b], 1u);
     });
@@ -215,10 +230,7 @@ static __global__ void k_count(MsmArgs a) {
 static __global__ void k_scatter(MsmArgs a) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.n || a.base_inf[i]) return;
-    uint32_t k[NLIMB];
-    const uint4 *p = reinterpret_cast<const uint4 *>(a.scalars + (size_t)i * NLIMB);
-    for (int q = 0; q < QUADS; ++q) { uint4 v = p[q]; k[4 * q] = v.x; k[4 * q + 1] = v.y; k[4 * q + 2] = v.z; k[4 * q + 3] = v.w; }
-    for_each_digit(k, a.c, a.Wd, [&](int w, int d) {
+    scalar_digits(a, i, [&](int w, int d) {
         uint32_t b = (uint32_t)(d < 0 ? -d : d) - 1u;
         uint32_t pos = atomicAdd(&a.cursor[(uint32_t)(w % a.W) * a.NB + b], 1u);
         a.entries[pos] = ((uint32_t)(w / a.W) * a.tab_stride + i) | (d < 0 ? 0x80000000u : 0u);

@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200_msm.h"
@@ -46,8 +47,14 @@ int main(int argc, char **argv) {
         const bool ok = pn > 0 && fread(image.data(), 1, (size_t)pn, pf) == (size_t)pn;
         fclose(pf);
         if (!ok) { fprintf(stderr, "cannot read %s\n", argv[3]); return 2; }
+        // one host thread per GPU: uploads and window-table builds of the shards run side by side
+        std::vector<int> rcs(gpus, 0);
+        std::vector<std::thread> loaders;
         for (int g = 0; g < gpus; ++g)
-            if (b200msm_key_load_shard(ctxs[g], image.data(), image.size(), g, gpus, &keys[g])) { fprintf(stderr, "%s\n", b200msm_last_error(ctxs[g])); return 2; }
+            loaders.emplace_back([&, g] { rcs[g] = b200msm_key_load_shard(ctxs[g], image.data(), image.size(), g, gpus, &keys[g]); });
+        for (auto &th : loaders) th.join();
+        for (int g = 0; g < gpus; ++g)
+            if (rcs[g]) { fprintf(stderr, "%s\n", b200msm_last_error(ctxs[g])); return 2; }
     }
     b200msm_key *key = keys[0];
     uint64_t info[2];

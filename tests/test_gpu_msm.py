@@ -114,7 +114,8 @@ def test_window_tables(ctxs, oracle, golden, curve, group):
             if want_sets == "one":
                 assert info["bucket_sets"] == 1 and info["tables"] > 1
             elif want_sets == "some":
-                assert info["tables"] == 5 and 1 < info["bucket_sets"] < 108
+                # G2 scalars are split in two halves (csrc/glv.cuh), each with its own tables: an even number of them
+                assert info["tables"] == (5 if group == 1 else 4) and 1 < info["bucket_sets"] < 108
             else:
                 assert info["tables"] == 1
             for n in (257, 100, 1):
