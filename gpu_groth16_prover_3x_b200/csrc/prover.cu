@@ -200,8 +200,9 @@ int prove_finish(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int n, cons
     const size_t in_words = (size_t)n * J1 + (size_t)n * J2 + (size_t)3 * n * J1;
     const size_t sc_words = fold_scratch_points((size_t)3 * n) * J2;               // scratch of the largest fold, in the larger point size
     const size_t out_words = 2 * A1 + A2;
-    if ((rc = tail_reserve(c0, (in_words + sc_words + 2 * J1 + J2 + out_words) * 4, std::max(in_words, out_words) * 4))) return rc;
     b200msm_ctx *ctx = c0;      // for CU()
+    CU(cudaSetDevice(c0->device));                 // the waits above left the last shard's device current
+    if ((rc = tail_reserve(c0, (in_words + sc_words + 2 * J1 + J2 + out_words) * 4, std::max(in_words, out_words) * 4))) return rc;
     TailBuf &t = c0->tail;
     uint32_t *h = reinterpret_cast<uint32_t *>(t.h);
     uint32_t *hA = h, *hB = hA + (size_t)n * J1, *hC = hB + (size_t)n * J2;
