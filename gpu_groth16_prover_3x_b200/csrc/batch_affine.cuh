@@ -296,12 +296,97 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
     const int lane = threadIdx.x & 31;
     const BaSlots s = {0, 1, 2, 3, 4, 5};
     const uint4 idle = make_uint4(REF_INF, REF_INF, 0u, 0u);
-    // ---- forward: denominators and prefix products
+    // ---- forward, unclassified: every pair is taken for a generic addition (x1 != x2), the denominators go straight
+    // into the running product.  A pair that is NOT generic -- equal abscissae (doubling, cancellation) or a copy --
+    // shows at the end: a zero product, or a descriptor without a second operand; the tile then runs the classified
+    // passes below instead.  With independent points that never happens, and the generic passes need no per-pair zero
+    // test (two team barriers in the towers), no classification parked in memory and 4 instead of 14 slot operations.
+    uint4 nxt, nxt2;
+    bool generic = true;
+    // d = (a1 - a2) * b.  Fq: the difference is formed inside the product (Team::mulsub).  Towers: every warp of the
+    // team reads all DEG coefficients of the first factor, so the fused form would subtract DEG times over; there the
+    // difference goes through the slab once (it replaces a1, which is dead or wanted as the difference in every use).
+    auto mul_diff = [&](int d, int a1, int a2, int b, bool pred) {
+        if (DEG == 1) T.mulsub(d, a1, a2, b, pred);
+        else { T.sub(a1, a1, a2); T.mul(d, a1, b, pred); }
+    };
+    auto mul_plain = [&](int d, int a1, int b) {
+        if (DEG == 1) T.mulsub(d, a1, -1, b); else T.mul(d, a1, b);
+    };
+    {
+        T.set_one(s.INV);
+        nxt = src.get(p0 + lane);
+        nxt2 = B > 1u ? src.get(p0 + 32u + lane) : idle;
+        for (uint32_t i = 0; i < B; ++i) {
+            const uint32_t p = p0 + i * 32u + lane;
+            const uint4 d = nxt;
+            const bool valid = d.x != REF_INF, has2 = d.y != REF_INF;
+            if (team_any(valid && !has2)) generic = false;
+            const uint32_t *g1 = ba_ref_ptr(a, d.x, AFFW), *g2 = ba_ref_ptr(a, d.y, AFFW);
+            nxt = nxt2;
+            if (nxt.x != REF_INF) {
+                prefetch_coord(T, ba_ref_ptr(a, nxt.x, AFFW));
+                if (nxt.y != REF_INF) prefetch_coord(T, ba_ref_ptr(a, nxt.y, AFFW));
+            }
+            nxt2 = i + 2 < B ? src.get(p + 64u) : idle;
+            BA_G2S_BEGIN();
+            BA_G2S(T, s.X1, g1, valid);
+            BA_G2S(T, s.X2, g2, has2);
+            BA_G2S_WAIT();
+            BA_S2G(T, a.scratch + (size_t)d.z * AFFW, s.INV, valid);                // exclusive prefix, parked in the output slot
+            mul_diff(s.INV, s.X2, s.X1, s.INV, valid && has2);
+        }
+        if (team_any(T.is_zero(s.INV))) generic = false;
+    }
+    if (generic) {
+        tile_inverse(T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
+        const uint32_t pl = p0 + (B - 1u) * 32u + lane;
+        nxt = src.get(pl);
+        nxt2 = B > 1u ? src.get(pl - 32u) : idle;
+        for (int i = (int)B - 1; i >= 0; --i) {
+            const uint32_t p = p0 + (uint32_t)i * 32u + lane;
+            const uint4 d = nxt;
+            const bool valid = d.x != REF_INF;
+            const uint32_t *g1 = ba_ref_ptr(a, d.x, AFFW), *g2 = ba_ref_ptr(a, d.y, AFFW);
+            uint32_t *out = a.scratch + (size_t)d.z * AFFW;
+            nxt = nxt2;
+            if (nxt.x != REF_INF) {
+                const uint32_t *n1 = ba_ref_ptr(a, nxt.x, AFFW), *n2 = ba_ref_ptr(a, nxt.y, AFFW);
+                prefetch_coord(T, n1); prefetch_coord(T, n1 + EW);
+                prefetch_coord(T, n2); prefetch_coord(T, n2 + EW);
+                prefetch_coord(T, a.scratch + (size_t)nxt.z * AFFW);
+            }
+            nxt2 = i > 1 ? src.get(p - 64u) : idle;
+            BA_G2S_BEGIN();
+            BA_G2S(T, s.X1, g1, valid);
+            BA_G2S(T, s.Y1, g1 + EW, valid);
+            BA_G2S(T, s.X2, g2, valid);
+            BA_G2S(T, s.Y2, g2 + EW, valid);
+            BA_G2S(T, s.PRE, out, valid);
+            BA_G2S_WAIT();
+            const bool n1 = valid && (d.x & REF_NEG) != 0u, n2 = valid && (d.y & REF_NEG) != 0u;
+            if (team_any(n1)) T.neg_if(s.Y1, s.Y1, n1, valid);
+            if (team_any(n2)) T.neg_if(s.Y2, s.Y2, n2, valid);
+            mul_plain(s.PRE, s.INV, s.PRE);               // 1 / d
+            mul_diff(s.INV, s.X2, s.X1, s.INV, valid);    // inverse of the shorter prefix (towers: X2 <- d)
+            mul_diff(s.Y2, s.Y2, s.Y1, s.PRE, true);      // lambda = (y2 - y1) / d
+            if (DEG == 3) T.sqr(s.PRE, s.Y2); else mul_plain(s.PRE, s.Y2, s.Y2);
+            if (DEG == 1) T.sub_sub(s.X2, s.PRE, s.X1, s.X2);                       // x3 = lambda^2 - x1 - x2
+            else { T.sub_sub(s.X2, s.PRE, s.X2, s.X1); T.sub(s.X2, s.X2, s.X1); }  //    = lambda^2 - d - 2 x1
+            mul_diff(s.PRE, s.X1, s.X2, s.Y2, true);      // lambda (x1 - x3)
+            T.sub(s.Y2, s.PRE, s.Y1);                     // y3
+            BA_S2G(T, out, s.X2, valid);
+            BA_S2G(T, out + EW, s.Y2, valid);
+            if (valid && T.comp == 0) nxt_refs[d.w] = REF_SCRATCH | d.z;
+        }
+        return;
+    }
+    // ---- forward, classified: denominators and prefix products
     T.set_one(s.INV);
     // descriptors are read two steps ahead and the coordinates of the next step are pulled into L2, so
     // that neither the list nor the gathers are waited for at DRAM latency
-    uint4 nxt = src.get(p0 + lane);
-    uint4 nxt2 = B > 1u ? src.get(p0 + 32u + lane) : idle;
+    nxt = src.get(p0 + lane);
+    nxt2 = B > 1u ? src.get(p0 + 32u + lane) : idle;
     for (uint32_t i = 0; i < B; ++i) {
         const uint32_t p = p0 + i * 32u + lane;
         const uint4 d = nxt;

@@ -135,6 +135,33 @@ struct Team {
         sync();
         MSM_FOR_COMP(c) st(d, c, res[MSM_CI(c)], pred);
     }
+    // d = (a1 - a2) * b, or a1 * b when a2 < 0: the difference is formed in registers on the way into the dot product
+    // (batch_affine.cuh: three of the five products of an affine addition take a difference, and a slot operation of
+    // its own costs a round trip through the slab).  One function for both forms keeps one copy of the product hot.
+#ifndef MNT753_HOST_EMU
+    __device__ __noinline__
+#endif
+    void mulsub(int d, int a1, int a2, int b, bool pred = true) const {
+        fq_t res[MSM_NCOMP];
+        sync();
+        MSM_FOR_COMP(c) {
+            uint32_t aa[DEG][NLIMB];
+            BQuads<DEG> src;
+            src.stride = LANES;
+#pragma unroll
+            for (int i = 0; i < DEG; ++i) {
+                ld(aa[i], a1, i);
+                if (a2 >= 0) { fq_t y; ld(y, a2, i); fq_sub<M>(aa[i], aa[i], y); }
+                if (i > c) fq_scale_unreduced(aa[i], aa[i], F::NR);
+                int j = c - i;
+                if (j < 0) j += DEG;
+                src.p[i] = elem(b, j);
+            }
+            fq_dot<M, DEG>(res[MSM_CI(c)], aa, src);
+        }
+        sync();
+        MSM_FOR_COMP(c) st(d, c, res[MSM_CI(c)], pred);
+    }
     // d = a^2.  Fq3 = Fq[u]/(u^3 - NR): the symmetric terms pair up, so every coefficient is a dot product of
     // length TWO (one lazy reduction) instead of three -- 1752 instead of 2328 MAC per warp:
     //     c0 = a0 a0 + (2 NR a1) a2      c1 = (2 a0) a1 + (NR a2) a2      c2 = (2 a0) a2 + a1 a1
@@ -174,6 +201,10 @@ struct Team {
     }
     MSM_OP void sub(int d, int a, int b, bool pred = true) const {
         MSM_FOR_COMP(c) { fq_t x, y; ld(x, a, c); ld(y, b, c); fq_sub<M>(x, x, y); st(d, c, x, pred); }
+    }
+    // d = a - b - c2
+    MSM_OP void sub_sub(int d, int a, int b, int c2, bool pred = true) const {
+        MSM_FOR_COMP(c) { fq_t x, y; ld(x, a, c); ld(y, b, c); fq_sub<M>(x, x, y); ld(y, c2, c); fq_sub<M>(x, x, y); st(d, c, x, pred); }
     }
     MSM_OP void dbl(int d, int a, bool pred = true) const {
         MSM_FOR_COMP(c) { fq_t x; ld(x, a, c); fq_add<M>(x, x, x); st(d, c, x, pred); }
