@@ -386,7 +386,7 @@ def run_b200(args):
     alg_bytes = float(n) * W * (2 * 96 * deg + 96 * deg + 2 * aff_bytes + 96 * deg + aff_bytes + 32 + 2)
     traffic = None
     if (curve, group, args.log_n) == (0, 1, 20):
-        for name in ("r02_k_batch_add_round0_traffic.json", "r01_k_batch_add_round0_traffic.json"):
+        for name in ("r02_k_batch_add_traffic.json", "r01_k_batch_add_round0_traffic.json"):
             try:
                 tj = json.load(open(os.path.join(ROOT, "profiles", name)))
                 traffic = {"bytes": tj["traffic_bytes"], "launch": tj["kernel"], "source": tj["source"],

@@ -53,7 +53,11 @@ const char *b200msm_last_error(const b200msm_ctx *ctx);
 int b200msm_bases_upload(b200msm_ctx *ctx, int group, const uint64_t *affine, size_t n, int *slot);
 int b200msm_bases_free(b200msm_ctx *ctx, int slot);
 /* Byte budget for the window tables of each base set uploaded afterwards (default 32 GiB; 0 = never
- * build tables, every MSM then runs the plain one-bucket-set-per-window Pippenger). */
+ * build tables, every MSM then runs the plain one-bucket-set-per-window Pippenger).
+ * G2 base sets with at least two tables use the twist Frobenius psi(P) = [q mod r] P (README.md:73 of the
+ * reference; libff G2::mul_by_q, mnt4753_g2.cpp:364-368): scalars are split k = k0 + k1 (q mod r) on the
+ * device, the tables come in two halves of equal size (an EVEN number of tables), and the upper half is psi of the
+ * lower half -- two multiplications by Fq constants per point instead of doublings and a normalisation. */
 int b200msm_set_table_budget(b200msm_ctx *ctx, size_t max_bytes_per_set);
 /* info[0] = points, [1] = window bits the tables were built for (0: none), [2] = tables NT,
  * [3] = bucket sets G, [4] = bytes resident, [5] = table build time in microseconds. */

@@ -133,6 +133,38 @@ def test_window_tables(ctxs, oracle, golden, curve, group):
         ctx.set_table_budget(32 << 30)
 
 
+@pytest.mark.parametrize("curve", [0, 1])
+def test_g2_split_scalars(ctxs, oracle, curve):
+    """G2 with window tables: scalars are split k = k0 + k1 (q mod r) on the device and the upper half of the tables is
+    psi of the lower half (csrc/glv.cuh).  Scalars around the places where the split changes shape -- 0, 1, r - 1, the
+    eigenvalue lam = q mod r and its neighbours, multiples of lam, -lam, values with k0 or k1 zero or negative -- on
+    single points and mixed into a random MSM, against the oracle's plain double-and-add / BDLO12."""
+    group = 2
+    r, q = po.fr_modulus(curve), po.fq_modulus(curve)
+    lam = q % r
+    deg = po.degree(curve, group)
+    n = 300                                     # >= 256: tables are built, so the split path runs
+    bases = oracle.gen_bases(curve, group, n)
+    special = [0, 1, 2, r - 1, r - 2, lam, lam - 1, lam + 1, (r - lam) % r, (2 * lam) % r, (lam * lam) % r, (lam * (lam - 1)) % r,
+               (1 << 376) % r, (1 << 377) % r, ((1 << 377) - 1) % r, (lam << 1) % r, (r - 1) // 2, (r + 1) // 2, pow(lam, -1, r)]
+    rng = np.random.default_rng(5 + curve)
+    ks = special + [int.from_bytes(rng.bytes(100), "little") % r for _ in range(n - len(special))]
+    sc = po.ints_to_array([k * po.R % r for k in ks])
+    ctx = ctxs[curve]
+    slot = ctx.upload_bases(group, bases)
+    try:
+        info = ctx.bases_info(slot)
+        assert info["tables"] > 1 and info["tables"] % 2 == 0
+        want, _ = oracle.msm(curve, group, bases, sc)
+        assert (affine(oracle, curve, group, ctx.msm(slot, sc, n)) == want).all()
+        for i in range(len(special)):           # one point at a time: k_i * P_i
+            want = oracle.point_op(curve, group, 3, bases[i * 24 * deg:(i + 1) * 24 * deg], k=sc[i * 12:(i + 1) * 12])
+            got = affine(oracle, curve, group, ctx.msm(slot, sc[i * 12:(i + 1) * 12], 1, offset=i))
+            assert (got == want).all(), i
+    finally:
+        ctx.free_bases(slot)
+
+
 @pytest.mark.parametrize("curve,group", CG)
 def test_giant_buckets_are_split_and_fixed_up(ctxs, oracle, curve, group):
     """The accumulation cuts the sorted list into shares at bucket boundaries, except for a bucket larger than
