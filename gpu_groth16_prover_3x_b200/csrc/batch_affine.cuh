@@ -203,10 +203,13 @@ __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
     return v;
 }
 
-// Plan of round r for one share (executed by ONE warp): lane per piece.  Every pair of consecutive references of a
-// piece becomes an addition appended to the share's pair list (an infinite operand short-circuits: the other one is
-// passed on, the pair is marked idle), an odd one out is carried over, the piece's count is halved.
-// Returns the number of pairs listed (idle ones included).
+// Plan of round r for one share (executed by ONE warp).  Pieces are taken 32 at a time, a lane per piece for its
+// bookkeeping (count halved, odd one out carried over); the PAIRS of those 32 pieces are then dealt over the lanes --
+// pair t of the group belongs to the piece whose running pair count first exceeds t, found by a five-step search over
+// the lanes -- so that a piece with thousands of points (a small window, the 0 / 1 wires of a witness, the top
+// window) is planned by the whole warp and not by one lane.  Every pair of consecutive references of a piece becomes
+// an addition appended to the share's pair list; an infinite operand turns it into a copy of the other one, two into
+// nothing.  Returns the number of pairs listed (idle ones included).
 __device__ __forceinline__ uint32_t ba_plan(const BaView &v, uint32_t r, int lane, uint32_t &maxc) {
     const uint32_t *cur = v.refs[r & 1u];
     uint32_t *nxt = v.refs[(r + 1u) & 1u];
@@ -223,24 +226,37 @@ __device__ __forceinline__ uint32_t ba_plan(const BaView &v, uint32_t r, int lan
         maxc = max(maxc, c);
         const uint32_t np = c >> 1;
         const uint32_t incl = warp_incl_scan(np, lane);
-        const uint32_t first = total + incl - np;
+        const uint32_t excl = incl - np, T = __shfl_sync(0xffffffffu, incl, 31);
         const uint32_t out0 = (r & 1u) ? v.b_base + ((ps + b + v.id) >> 2) : v.a_base + (ps >> 1);
-        for (uint32_t j = 0; j < np; ++j) {
-            const uint32_t r1 = cur[ps + 2u * j], r2 = cur[ps + 2u * j + 1u];
-            // An infinite operand: the other one is COPIED to the pair's output slot (d.y = REF_INF), not passed on by
-            // reference -- a reference handed through would outlive the round its slot is reserved for (the slot
-            // scheme above recycles a piece's slots every second round) and be overwritten under the reader.
-            uint4 d;
-            if (r1 == REF_INF && r2 == REF_INF) {
-                nxt[ps + j] = REF_INF;
-                d = make_uint4(REF_INF, REF_INF, 0u, 0u);
-            } else if (r1 == REF_INF) d = make_uint4(r2, REF_INF, out0 + j, ps + j);
-            else d = make_uint4(r1, r2, out0 + j, ps + j);
-            v.pairs[first + j] = d;
-        }
         if (c & 1u) nxt[ps + np] = cur[ps + c - 1u];
         if (valid) v.cntv[b + v.id] = (c + 1u) >> 1;
-        total += __shfl_sync(0xffffffffu, incl, 31);
+        for (uint32_t t0 = 0; t0 < T; t0 += 32u) {
+            const uint32_t t = t0 + (uint32_t)lane;
+            int l = 0;                                   // lanes whose running count is <= t = the pair's piece
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                const uint32_t probe = __shfl_sync(0xffffffffu, incl, l + step - 1);
+                if (probe <= t) l += step;
+            }
+            const int src = l < 32 ? l : 31;
+            const uint32_t pps = __shfl_sync(0xffffffffu, ps, src), pex = __shfl_sync(0xffffffffu, excl, src);
+            const uint32_t pout = __shfl_sync(0xffffffffu, out0, src);
+            if (t < T) {
+                const uint32_t j = t - pex;
+                const uint32_t r1 = cur[pps + 2u * j], r2 = cur[pps + 2u * j + 1u];
+                // An infinite operand: the other one is COPIED to the pair's output slot (d.y = REF_INF), not passed on
+                // by reference -- a reference handed through would outlive the round its slot is reserved for (the slot
+                // scheme recycles a piece's slots every second round) and be overwritten under the reader.
+                uint4 d;
+                if (r1 == REF_INF && r2 == REF_INF) {
+                    nxt[pps + j] = REF_INF;
+                    d = make_uint4(REF_INF, REF_INF, 0u, 0u);
+                } else if (r1 == REF_INF) d = make_uint4(r2, REF_INF, pout + j, pps + j);
+                else d = make_uint4(r1, r2, pout + j, pps + j);
+                v.pairs[total + t] = d;
+            }
+        }
+        total += T;
     }
     return total;
 }

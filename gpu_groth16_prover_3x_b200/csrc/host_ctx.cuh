@@ -3,6 +3,7 @@
 // A, B1, B2 and L multiexps of one proof can be in flight together, as the reference does with one
 // stream per MSM (cuda_prover_piecewise.cu:162-167).
 #pragma once
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -120,15 +121,15 @@ int fail(b200msm_ctx *ctx, int code, const char *fmt, ...) {
 inline int degree_of(int curve, int group) { return group == B200MSM_G1 ? 1 : (curve == B200MSM_MNT4753 ? 2 : 3); }
 
 // ---- window-size / table choice ---------------------------------------------------------------
-// Time model in nanoseconds, calibrated on B200 (profiles/r02_size_sweep_1gpu.txt, tools/c_sweep.py): ~1.05 ns per
-// batched-affine addition (one per point and digit; x3 / x6 in the towers), ~0.15 ms of latency per round of the
-// accumulation (a tile inversion and two passes), and for the bucket reduction (bucket_tree.cuh) ~2.2 ns per bucket
-// in its affine rounds, ~0.11 ms per tree level, ~35 us per doubling of the final terms (c - 2 of them, serial) and
-// ~0.7 ms for the butterflies of the short lists and the window sum; bucket sets after the first cost c doublings each
-// in the window combine.  The number of accumulation rounds is log2 of the LARGEST bucket: besides the average
-// occupancy that is the top window, which holds only rem = 754 - (Wd - 1) c bits and therefore piles n / 2^(rem-1)
-// points on each of its few buckets (c = 16: rem = 2, a quarter of all points in one bucket) -- widths with a short
-// top window lose.
+// Time model in nanoseconds, calibrated on B200 (profiles/r02_c_sweep.txt, profiles/r02_size_sweep_1gpu.txt): ~1.0 ns per
+// batched-affine addition (one per point and digit; x3 / x6 in the towers); ~0.3 ms per round of the accumulation
+// (plan, tile inversion, two passes -- its time follows the NUMBER OF ROUNDS much more than the number of additions
+// below 2^18 points: 2^12 points take 2.9 ms at c = 12 and 0.8 ms at c = 18); the bucket reduction (bucket_tree.cuh)
+// ~3 ns per bucket, ~0.1 ms per tree level, ~30 us per doubling of the final terms and ~0.45 ms for the butterflies of
+// the short lists and the window sum; bucket sets after the first cost c doublings each in the window combine.
+// Rounds = log2 of the LARGEST bucket: a typical one, and the top window's, which holds only rem = 754 - (Wd - 1) c
+// bits and therefore piles n / 2^(rem-1) points on each of its few buckets (c = 16: rem = 2, a quarter of all points
+// in one bucket).
 struct TabCfg { int c, Wd, NT, G; bool glv; };
 inline int digits_for(int c) { return (MNT753_NUM_BITS + 1 + c - 1) / c; }
 inline int half_digits_for(int c) { return (MNT753_GLV_HALF_BITS + 1 + c - 1) / c; }   // of one half of a split G2 scalar
@@ -170,12 +171,17 @@ inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bo
         const double NB = double(1u << (c - 1));
         const double avg = double(n) * NT / NB;                                     // digits per bucket of a set
         const double top = (rem >= c || rem <= 0) ? 0.0 : double(n) / double(1u << (rem > 1 ? rem - 1 : 0));
-        double rounds = 1.0;
-        for (double occ = avg + top; occ > 1.0; occ *= 0.5) rounds += 1.0;
+        // rounds = log2 of the largest bucket: of a typical one (Poisson tail over the average occupancy), which every
+        // share goes through, plus the further ones of the top window's overfull buckets, which only the shares holding
+        // their pieces run (and whose keys contend in the sort)
+        const double typical = avg + 4.0 * sqrt(avg) + 3.0;
+        double rounds = 1.0, rounds_top = 0.0;
+        for (double occ = typical; occ > 1.0; occ *= 0.5) rounds += 1.0;
+        for (double occ = (typical + top) / typical; occ > 1.0; occ *= 0.5) rounds_top += 1.0;
         const double lat = deg == 1 ? 1.0 : (deg == 2 ? 1.4 : 1.9);               // latency of one field operation in the towers
         const double levels = c > 6 ? double(c - 6) : 0.0;
-        const double cost = double(Wd) * double(n) * 1.05 * k + rounds * 150000.0 * lat +
-                            double(G) * NB * 2.2 * k + (levels * 110000.0 + 700000.0 + double(c) * 35000.0) * lat +
+        const double cost = double(Wd) * double(n) * 1.0 * k + (rounds * 300000.0 + rounds_top * 200000.0) * lat +
+                            double(G) * NB * 3.0 * k + (levels * 100000.0 + 450000.0 + double(c) * 30000.0) * lat +
                             double(G - 1) * c * 35000.0 * lat;
         if (cost < best_cost) { best_cost = cost; best = {c, Wd, NT, G, glv}; }
     }
