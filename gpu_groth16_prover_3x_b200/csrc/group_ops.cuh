@@ -19,17 +19,17 @@ struct DevBuf {
 // Jacobian additions are dearer in proportion (measured: profiles/r02_ab_tree_threshold.txt)
 constexpr uint64_t TREE_AFFINE_MIN = B200_TREE_AFFINE_MIN;
 
-// teams that take a share of an MSM with at most `emax` sorted entries: every team of the persistent grid, but no
-// share below 256 entries (eight additions per lane: below that a round is all fixed cost)
+// teams that take a share of an MSM with at most `emax` sorted entries on `sms` SMs: every team of the persistent grid,
+// but no share below 256 entries (eight additions per lane: below that a round is all fixed cost)
 template <class G>
-uint32_t shares_for(const b200msm_ctx *ctx, uint64_t emax) {
-    const uint64_t teams = (uint64_t)ctx->sm_count * BaCfg<G>::TPB;
+uint32_t shares_for(int sms, uint64_t emax) {
+    const uint64_t teams = (uint64_t)sms * BaCfg<G>::TPB;
     if (const char *e = getenv("B200MSM_SHARES")) return (uint32_t)std::max(1, atoi(e));   // development knob
     return (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(teams, emax / 256));
 }
 
 template <class G>
-Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) {
+Plan make_plan(int sms, size_t n, const TabCfg &cfg, char *base) {
     constexpr size_t JACB = 3 * G::F::DEG * NLIMB * 4, AFFB = 2 * G::F::DEG * NLIMB * 4;
     Plan p;
     MsmArgs &a = p.a;
@@ -59,7 +59,7 @@ Plan make_plan(const b200msm_ctx *ctx, size_t n, const TabCfg &cfg, char *base) 
     // batched-affine accumulation: reference lists, sums of even rounds (region A: a piece starting at list entry
     // e puts sum j at (e >> 1) + j), of odd rounds (region B: ((e + bucket + share) >> 2) + j), the fix-up's own
     // small regions, pair list and codes (share t starts at (E0 >> 1) + t)
-    const uint32_t U = shares_for<G>(ctx, emax);
+    const uint32_t U = shares_for<G>(sms, emax);
     const uint64_t capA = emax / 2 + 1, capB = (emax + a.K + U) / 4 + 2, capF = 2 * (uint64_t)U + 2;
     // bucket-reduction tree (bucket_tree.cuh): a reference and a scratch slot per node, 2 NB nodes per set
     TreeArgs &t = p.t;
@@ -149,20 +149,13 @@ int grow_arena(b200msm_ctx *ctx, Lane &ln, size_t bytes) {
     return B200MSM_OK;
 }
 
-template <class G>
-TabCfg cfg_for(const b200msm_ctx *ctx, const BaseSet &bs, size_t n) {
-    // window tables are used when they exist and the caller did not force a different window width
-    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) return TabCfg{bs.c_tab, bs.Wd, bs.NT, bs.G, bs.glv};
-    return choose_cfg(n, G::F::DEG, ctx->c_override, 0, false);
-}
-
 // Size lane `li`'s arena for MSMs of n points over `bs` and set the kernels' shared-memory attributes now, so
 // that the first MSM does not pay for them (b200msm_key_load warms every lane it is going to use).
 template <class G>
 int reserve_lane(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t n) {
     int rc = prepare_kernels<G>(ctx);
     if (rc || n == 0) return rc;
-    Plan probe = make_plan<G>(ctx, n, cfg_for<G>(ctx, bs, n), nullptr);
+    Plan probe = make_plan<G>(ctx->sm_count, n, cfg_for_set(ctx, bs, n), nullptr);   // all SMs: the most shares, the largest arena
     return grow_arena(ctx, ctx->lanes[li], probe.bytes);
 }
 
@@ -195,18 +188,20 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
         return B200MSM_OK;
     }
 
-    const TabCfg cfg = cfg_for<G>(ctx, bs, n);
+    const TabCfg cfg = cfg_for_set(ctx, bs, n);
     const int c = cfg.c;
+    // the SMs this lane may occupy (b200msm_set_lane_sms): persistent grids and the number of shares follow it
+    const int sms = lane_sm_cap(ctx, li);
     // 32-bit positions in the sorted list and 30-bit table rows (reference = row | scratch << 30 | sign << 31)
     if ((uint64_t)n * (uint64_t)cfg.Wd >= (uint64_t(1) << 32) - 4096 || (uint64_t)bs.n * (uint64_t)cfg.NT >= (uint64_t(1) << 30))
         return fail(ctx, B200MSM_ERR_ARG, "n = %zu with %d digits per scalar exceeds the 2^32 sorted entries / 2^30 table rows of one call; shard the MSM", n, cfg.Wd);
     int rc = prepare_kernels<G>(ctx);
     if (rc) return rc;
-    Plan probe = make_plan<G>(ctx, n, cfg, nullptr);
+    Plan probe = make_plan<G>(sms, n, cfg, nullptr);
     if (probe.slots >= (uint64_t(1) << 30))
         return fail(ctx, B200MSM_ERR_ARG, "n = %zu with %d digits per scalar needs %llu scratch points (limit 2^30 per call); shard the MSM", n, cfg.Wd, (unsigned long long)probe.slots);
     if ((rc = grow_arena(ctx, ln, probe.bytes))) return rc;
-    Plan p = make_plan<G>(ctx, n, cfg, ln.arena);
+    Plan p = make_plan<G>(sms, n, cfg, ln.arena);
     MsmArgs &a = p.a;
     BaArgs &b = p.b;
     a.bases = bs.pts + offset * AFFW;
@@ -223,6 +218,10 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     cudaGetLastError();
     const int nchunk = (!on_device && n >= (size_t(1) << 16)) ? NCOPY : 1;
     CU(cudaMemsetAsync(a.count, 0, (size_t)a.K * 4, st));
+    if (nchunk > 1 && !ln.copy_stream) {      // created on first use: a lane that only sees device scalars never needs it
+        CU(cudaStreamCreateWithFlags(&ln.copy_stream, cudaStreamNonBlocking));
+        for (int e = 0; e <= NCOPY; ++e) CU(cudaEventCreateWithFlags(&ln.ev_copy[e], cudaEventDisableTiming));
+    }
     if (nchunk > 1) {
         CU(cudaEventRecord(ln.ev_copy[NCOPY], st));                 // the arena is free once earlier work on st is done
         CU(cudaStreamWaitEvent(ln.copy_stream, ln.ev_copy[NCOPY], 0));
@@ -257,7 +256,7 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
     CU(cudaMemsetAsync(b.ctl, 0, (size_t)BA_CTL_WORDS * 4, st));
     CU(cudaMemsetAsync(b.bucket_ref, 0xff, (size_t)a.K * 4, st));
     CU(cudaMemsetAsync(b.bnd_bucket, 0xff, (size_t)2 * b.U * 4, st));
-    const unsigned ba_blocks = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count, (uint64_t)b.U);   // shares are dealt round-robin over the blocks
+    const unsigned ba_blocks = (unsigned)std::min<uint64_t>((uint64_t)sms, (uint64_t)b.U);   // shares are dealt round-robin over the blocks
     k_batch_add<G><<<ba_blocks, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
     k_ba_fixup<G><<<1, BC::TS::THREADS, BC::TS::SMEM, st>>>(b);
     launches += 2;
@@ -272,8 +271,8 @@ int enqueue_msm(b200msm_ctx *ctx, int li, const BaseSet &bs, size_t offset, cons
             t.logq = t.k - (r + 1);
             t.P = t.W * t.q * (2u + r);
             if (r <= t.hA) {
-                const uint64_t teams = std::min<uint64_t>((uint64_t)ctx->sm_count * BC::TPB, ((uint64_t)t.P + 31) / 32);
-                const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)ctx->sm_count, teams);
+                const uint64_t teams = std::min<uint64_t>((uint64_t)sms * BC::TPB, ((uint64_t)t.P + 31) / 32);
+                const unsigned blocks = (unsigned)std::min<uint64_t>((uint64_t)sms, teams);
                 k_tree_round<G><<<blocks, BC::TS::THREADS, BC::TS::SMEM, st>>>(b, t);
             } else {
                 const unsigned lanes = TC::TPB * 32;

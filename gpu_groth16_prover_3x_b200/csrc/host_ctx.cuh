@@ -1,7 +1,7 @@
 // Host-side state shared by the translation units of libb200msm.so (msm.cu holds the C ABI, inst_*.cu
-// the per-group kernels).  One context per (curve, GPU); four internal streams ("lanes") so that the
-// A, B1, B2 and L multiexps of one proof can be in flight together, as the reference does with one
-// stream per MSM (cuda_prover_piecewise.cu:162-167).
+// the per-group kernels).  One context per (curve, GPU); five internal streams ("lanes"), one per query of a
+// proof, so that the A, B1, B2 and L multiexps can be in flight together, as the reference does with one stream
+// per MSM (cuda_prover_piecewise.cu:162-167), and the H query can follow its FFTs without waiting for any of them.
 #pragma once
 #include <cmath>
 #include <cstdarg>
@@ -20,7 +20,7 @@
 
 using namespace mnt753;
 
-constexpr int NLANES = 4;
+constexpr int NLANES = 5;
 constexpr int NEVENTS = 7;
 constexpr int NCOPY = 4;     // chunks of a host-scalar upload
 
@@ -93,6 +93,7 @@ struct b200msm_ctx {
     size_t table_budget = size_t(32) << 30;  // bytes of window tables per base set (0: never build tables)
     std::vector<BaseSet> sets;
     Lane lanes[NLANES];
+    int lane_sms[NLANES] = {0, 0, 0, 0, 0};     // SMs the MSMs of a lane may occupy (0: all of them), b200msm_set_lane_sms
     FftState fft;
     TailBuf tail;
     std::string err = "";
@@ -134,8 +135,34 @@ struct TabCfg { int c, Wd, NT, G; bool glv; };
 inline int digits_for(int c) { return (MNT753_NUM_BITS + 1 + c - 1) / c; }
 inline int half_digits_for(int c) { return (MNT753_GLV_HALF_BITS + 1 + c - 1) / c; }   // of one half of a split G2 scalar
 
-inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bool tables) {
+// The model's two terms for one MSM of n points in a configuration: `work_ns` shrinks with the SMs the MSM runs on
+// (additions, per-bucket work of the reduction), `latency_ns` does not (rounds, tree levels, the serial tail).
+struct MsmCost { double work_ns, latency_ns; };
+inline MsmCost model_cost(size_t n, int deg, const TabCfg &cfg) {
     const double k = deg == 1 ? 1.0 : (deg == 2 ? 3.0 : 6.0);
+    const int c = cfg.c;
+    // bits of the top window (of a half's top window for split scalars; <= 0: it stays empty)
+    const int rem = cfg.glv ? MNT753_GLV_HALF_BITS + 1 - (cfg.Wd / 2 - 1) * c : MNT753_NUM_BITS + 1 - (cfg.Wd - 1) * c;
+    const double NB = double(1u << (c - 1));
+    const double avg = double(n) * cfg.NT / NB;                                 // digits per bucket of a set
+    const double top = (rem >= c || rem <= 0) ? 0.0 : double(n) / double(1u << (rem > 1 ? rem - 1 : 0));
+    // rounds = log2 of the largest bucket: of a typical one (Poisson tail over the average occupancy), which every
+    // share goes through, plus the further ones of the top window's overfull buckets, which only the shares holding
+    // their pieces run (and whose keys contend in the sort)
+    const double typical = avg + 4.0 * sqrt(avg) + 3.0;
+    double rounds = 1.0, rounds_top = 0.0;
+    for (double occ = typical; occ > 1.0; occ *= 0.5) rounds += 1.0;
+    for (double occ = (typical + top) / typical; occ > 1.0; occ *= 0.5) rounds_top += 1.0;
+    const double lat = deg == 1 ? 1.0 : (deg == 2 ? 1.4 : 1.9);               // latency of one field operation in the towers
+    const double levels = c > 6 ? double(c - 6) : 0.0;
+    MsmCost m;
+    m.work_ns = double(cfg.Wd) * double(n) * 1.0 * k + double(cfg.G) * NB * 3.0 * k;
+    m.latency_ns = (rounds * 300000.0 + rounds_top * 200000.0) * lat + (levels * 100000.0 + 450000.0 + double(c) * 30000.0) * lat +
+                   double(cfg.G - 1) * c * 35000.0 * lat;
+    return m;
+}
+
+inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bool tables) {
     const size_t affb = (size_t)2 * deg * NLIMB * 4;
     TabCfg best = {2, digits_for(2), 1, digits_for(2), false};
     double best_cost = 1e300;
@@ -150,42 +177,42 @@ inline TabCfg choose_cfg(size_t n, int deg, int c_fixed, size_t budget_bytes, bo
         }
         // G2 with at least two tables: split scalars (glv.cuh) -- two halves of Wh digits, Wh a multiple of the
         // number of bucket sets so that a table belongs to one half
-        bool glv = false;
-        int G, NT, rem;
+        TabCfg cfg;
+        cfg.c = c;
         if (deg > 1 && nt >= 2) {
             int Wh = half_digits_for(c);
             if (nt > (size_t)(2 * Wh)) nt = 2 * Wh;
             nt &= ~size_t(1);                                                      // the two halves have the same number of tables
-            G = (2 * Wh + (int)nt - 1) / (int)nt;
-            Wh = (Wh + G - 1) / G * G;
-            Wd = 2 * Wh;
-            NT = Wd / G;
-            glv = true;
-            rem = MNT753_GLV_HALF_BITS + 1 - (Wh - 1) * c;                        // bits of a half's top window (<= 0: it stays empty)
+            cfg.G = (2 * Wh + (int)nt - 1) / (int)nt;
+            Wh = (Wh + cfg.G - 1) / cfg.G * cfg.G;
+            cfg.Wd = 2 * Wh;
+            cfg.NT = cfg.Wd / cfg.G;
+            cfg.glv = true;
         } else {
             if (nt > (size_t)Wd) nt = Wd;
-            G = (Wd + (int)nt - 1) / (int)nt;
-            NT = (Wd + G - 1) / G;
-            rem = MNT753_NUM_BITS + 1 - (Wd - 1) * c;                             // bits of the top window
+            cfg.Wd = Wd;
+            cfg.G = (Wd + (int)nt - 1) / (int)nt;
+            cfg.NT = (Wd + cfg.G - 1) / cfg.G;
+            cfg.glv = false;
         }
-        const double NB = double(1u << (c - 1));
-        const double avg = double(n) * NT / NB;                                     // digits per bucket of a set
-        const double top = (rem >= c || rem <= 0) ? 0.0 : double(n) / double(1u << (rem > 1 ? rem - 1 : 0));
-        // rounds = log2 of the largest bucket: of a typical one (Poisson tail over the average occupancy), which every
-        // share goes through, plus the further ones of the top window's overfull buckets, which only the shares holding
-        // their pieces run (and whose keys contend in the sort)
-        const double typical = avg + 4.0 * sqrt(avg) + 3.0;
-        double rounds = 1.0, rounds_top = 0.0;
-        for (double occ = typical; occ > 1.0; occ *= 0.5) rounds += 1.0;
-        for (double occ = (typical + top) / typical; occ > 1.0; occ *= 0.5) rounds_top += 1.0;
-        const double lat = deg == 1 ? 1.0 : (deg == 2 ? 1.4 : 1.9);               // latency of one field operation in the towers
-        const double levels = c > 6 ? double(c - 6) : 0.0;
-        const double cost = double(Wd) * double(n) * 1.0 * k + (rounds * 300000.0 + rounds_top * 200000.0) * lat +
-                            double(G) * NB * 3.0 * k + (levels * 100000.0 + 450000.0 + double(c) * 30000.0) * lat +
-                            double(G - 1) * c * 35000.0 * lat;
-        if (cost < best_cost) { best_cost = cost; best = {c, Wd, NT, G, glv}; }
+        const MsmCost m = model_cost(n, deg, cfg);
+        const double cost = m.work_ns + m.latency_ns;
+        if (cost < best_cost) { best_cost = cost; best = cfg; }
     }
     return best;
+}
+
+// configuration of an MSM of n points over a resident base set: its window tables are used when they exist and the
+// caller did not force a different window width
+inline TabCfg cfg_for_set(const b200msm_ctx *ctx, const BaseSet &bs, size_t n) {
+    if (bs.c_tab && (ctx->c_override == 0 || ctx->c_override == bs.c_tab)) return TabCfg{bs.c_tab, bs.Wd, bs.NT, bs.G, bs.glv};
+    return choose_cfg(n, degree_of(ctx->curve, bs.group), ctx->c_override, 0, false);
+}
+
+// SMs the MSMs of lane `li` may occupy
+inline int lane_sm_cap(const b200msm_ctx *ctx, int li) {
+    const int s = ctx->lane_sms[li];
+    return (s > 0 && s < ctx->sm_count) ? s : ctx->sm_count;
 }
 
 // make the context's tail buffers at least this large (contents are not preserved)

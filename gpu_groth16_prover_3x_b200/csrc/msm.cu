@@ -1,8 +1,10 @@
-// Host side of the engine: the C ABI of include/b200_msm.h.  One context per (curve, GPU); four
-// internal streams ("lanes") so that the A, B1, B2 and L multiexps of one proof can be in flight
+// Host side of the engine: the C ABI of include/b200_msm.h.  One context per (curve, GPU); five
+// internal streams ("lanes"), one per query of a proof, so that its multiexps can be in flight
 // together, as the reference does with one stream per MSM (cuda_prover_piecewise.cu:162-167).  No CPU
 // fallback: every failure is reported through the return code and b200msm_last_error().
 // The kernels are instantiated per group in inst_*.cu and reached through GroupOps (group_ops.cuh).
+#include <cstdlib>
+
 #include "host_ctx.cuh"
 
 extern const GroupOps b200msm_ops_mnt4g1, b200msm_ops_mnt4g2, b200msm_ops_mnt6g1, b200msm_ops_mnt6g2;
@@ -169,6 +171,13 @@ extern "C" {
 int b200msm_create(int curve, int device, b200msm_ctx **out) {
     if (!out || (curve != B200MSM_MNT4753 && curve != B200MSM_MNT6753)) return B200MSM_ERR_ARG;
     *out = nullptr;
+    // A context runs up to eight streams at once (five lanes, the FFTs, the witness upload, the proof tail) plus the
+    // copy streams of chunked scalar uploads.  The driver maps streams onto 8 hardware queues by default and streams
+    // that share a queue wait for each other: the H query, enqueued on its own lane the moment its FFTs were done,
+    // started only when the A query's kernels had drained (measured with B200MSM_TRACE).  More queues, unless the
+    // caller chose a number; it takes effect when this is the process's first CUDA call (b200_prove), and is harmless
+    // otherwise.
+    setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
     int count = 0;
     if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return B200MSM_ERR_CUDA;
     b200msm_ctx *ctx = new b200msm_ctx;
@@ -185,8 +194,6 @@ int b200msm_create(int curve, int device, b200msm_ctx **out) {
         bool ok = cudaStreamCreateWithFlags(&ln.own_stream, cudaStreamNonBlocking) == cudaSuccess;
         ln.stream = ln.own_stream;
         for (int e = 0; e < NEVENTS && ok; ++e) ok = cudaEventCreate(&ln.ev[e]) == cudaSuccess;
-        ok = ok && cudaStreamCreateWithFlags(&ln.copy_stream, cudaStreamNonBlocking) == cudaSuccess;
-        for (int e = 0; e <= NCOPY && ok; ++e) ok = cudaEventCreateWithFlags(&ln.ev_copy[e], cudaEventDisableTiming) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_result, 3 * 3 * NLIMB * 4) == cudaSuccess;
         ok = ok && cudaMallocHost(&ln.h_ctl, BA_CTL_WORDS * 4) == cudaSuccess;
         if (!ok) { b200msm_destroy(ctx); return B200MSM_ERR_CUDA; }
@@ -346,6 +353,13 @@ int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream) {
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ln.stream));
     ln.stream = cuda_stream ? (cudaStream_t)cuda_stream : ln.own_stream;
+    return B200MSM_OK;
+}
+
+int b200msm_set_lane_sms(b200msm_ctx *ctx, int lane, int sms) {
+    if (!ctx) return B200MSM_ERR_ARG;
+    if (lane < 0 || lane >= NLANES) return fail(ctx, B200MSM_ERR_ARG, "lane %d out of range", lane);
+    ctx->lane_sms[lane] = (sms > 0 && sms < ctx->sm_count) ? sms : 0;
     return B200MSM_OK;
 }
 

@@ -6,7 +6,10 @@
 //     (the reference: libff on the host, lines 198-204),
 // writing the proof bytes of groth16_output_write (A || B || C, affine, infinity as zeros;
 // libsnark/serialization.hpp:43-67).  It only composes the other entry points of include/b200_msm.h.
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -22,6 +25,7 @@ struct b200msm_key {
     uint32_t *h_dev = nullptr;           // shards > 0: their slice of the H coefficients (copied from shard 0's GPU)
     cudaStream_t stream = nullptr;
     cudaEvent_t ready = nullptr;
+    cudaEvent_t t0 = nullptr;            // start of the proof on this shard (B200MSM_TRACE=1: per-lane timeline)
 };
 
 int b200msm_internal_fr_scale(b200msm_ctx *ctx, size_t n, const uint32_t *in_dev, const uint32_t *k_dev, uint32_t *out_dev, cudaStream_t st);
@@ -31,6 +35,30 @@ const GroupOps &b200msm_internal_ops(int curve, int group);
 
 namespace {
 inline int g2_deg(const b200msm_ctx *ctx) { return ctx->curve == B200MSM_MNT4753 ? 2 : 3; }
+
+// One pass over every kernel a proof launches, on zeros: a small MSM per query on its lane and, on shard 0, compute_H.
+// The CUDA runtime loads a kernel at its FIRST launch and that load waits for the kernels already running; with the
+// queries of a proof side by side on persistent kernels (lane_split_plan below) the first proof would serialise on
+// those loads -- measured: 47 ms for the first MNT6753 default proof against 31 ms for the following ones.
+int key_warm_up(b200msm_ctx *ctx, const b200msm_key *key) {
+    const size_t nw = 1024, fft_n = key->shard == 0 ? key->d + 1 : 0;
+    void *zeros = nullptr;
+    const size_t bytes = std::max<size_t>(nw, 3 * fft_n) * 96;
+    CU(cudaMalloc(&zeros, bytes));
+    int rc = B200MSM_OK;
+    uint64_t out[5][108];
+    if (cudaMemset(zeros, 0, bytes) != cudaSuccess) rc = fail(ctx, B200MSM_ERR_CUDA, "cudaMemset failed");
+    for (int q = 0; q < 5 && !rc; ++q)
+        rc = b200msm_msm_async(ctx, q, key->slot[q], 0, static_cast<const uint64_t *>(zeros), std::min(nw, key->cnt[q]), out[q]);
+    if (!rc && fft_n) {
+        const uint64_t *z = static_cast<const uint64_t *>(zeros), *h = nullptr;
+        rc = b200msm_compute_h(ctx, key->d, z, z + fft_n * 12, z + 2 * fft_n * 12, nullptr, &h);
+    }
+    for (int q = 0; q < 5; ++q)
+        if (ctx->lanes[q].pending) { const int rcw = b200msm_wait(ctx, q); if (!rc) rc = rcw; }
+    cudaFree(zeros);
+    return rc;
+}
 }
 
 extern "C" {
@@ -45,6 +73,7 @@ void b200msm_key_free(b200msm_ctx *ctx, b200msm_key *key) {
     if (key->r_dev) cudaFree(key->r_dev);
     if (key->h_dev) cudaFree(key->h_dev);
     if (key->ready) cudaEventDestroy(key->ready);
+    if (key->t0) cudaEventDestroy(key->t0);
     if (key->stream) cudaStreamDestroy(key->stream);
     delete key;
 }
@@ -83,16 +112,17 @@ int b200msm_key_load_shard(b200msm_ctx *ctx, const void *params_image, size_t by
     bool ok = cudaMalloc(&key->w_dev, (key->w_cnt + 1) * 96) == cudaSuccess && cudaMalloc(&key->rw_dev, (key->cnt[0] + 1) * 96) == cudaSuccess &&
               cudaMalloc(&key->r_dev, 96) == cudaSuccess &&
               cudaStreamCreateWithFlags(&key->stream, cudaStreamNonBlocking) == cudaSuccess &&
-              cudaEventCreateWithFlags(&key->ready, cudaEventDisableTiming) == cudaSuccess;
+              cudaEventCreateWithFlags(&key->ready, cudaEventDisableTiming) == cudaSuccess && cudaEventCreate(&key->t0) == cudaSuccess;
     if (ok && shard > 0) ok = cudaMalloc(&key->h_dev, (key->cnt[4] + 1) * 96) == cudaSuccess;
     if (!ok) { b200msm_key_free(ctx, key); return fail(ctx, B200MSM_ERR_OOM, "cannot allocate the witness buffers"); }
-    // warm everything the first proof would otherwise pay for: lane arenas (A and H share lane 0), domain tables
+    // warm everything the first proof would otherwise pay for: lane arenas (query q runs on lane q), domain tables
     int rc = b200msm_internal_reserve(ctx, 0, key->slot[0], key->cnt[0]);
-    if (!rc) rc = b200msm_internal_reserve(ctx, 0, key->slot[4], key->cnt[4]);
+    if (!rc) rc = b200msm_internal_reserve(ctx, 4, key->slot[4], key->cnt[4]);
     if (!rc) rc = b200msm_internal_reserve(ctx, 1, key->slot[1], key->cnt[1]);
     if (!rc) rc = b200msm_internal_reserve(ctx, 2, key->slot[2], key->cnt[2]);
     if (!rc) rc = b200msm_internal_reserve(ctx, 3, key->slot[3], key->cnt[3]);
     if (!rc && shard == 0) rc = b200msm_internal_fft_prepare(ctx, d);
+    if (!rc) rc = key_warm_up(ctx, key);
     if (rc) { b200msm_key_free(ctx, key); return rc; }
     *out = key;
     return B200MSM_OK;
@@ -140,12 +170,116 @@ size_t b200msm_input_bytes(const b200msm_key *key) { return key ? ((key->m + 1) 
 namespace {
 struct Partials { uint64_t A[36], rB1[36], B2[108], L[36], H[36]; };
 
+// ---- the five MSMs of a proof side by side -----------------------------------------------------------------------
+// The accumulation and the first reduction rounds of an MSM are persistent kernels of one block per SM, so MSMs
+// enqueued on different lanes still run one after the other, each paying the latency of its rounds, of its reduction
+// tree and of the serial tail on a GPU that is mostly idle (a 2^15-point G1 MSM: 5.4 ms, of which about 1 ms is
+// arithmetic).  When the proof is small the lanes get DISJOINT parts of the GPU instead (b200msm_set_lane_sms).
+// Five parties: the A, B1, B2 and L queries (lanes 0-3) and, on lane 4, the H query behind the FFTs of compute_H,
+// which run on the SMs that lane 4 is going to use.  With work W_q (shrinks with the SMs) and latency L_q (does not)
+// from the window-choice model, party q gets the fraction W_q / (T - L_q) of the SMs, T being the common finishing
+// time that makes the fractions sum to one.  B200MSM_LANE_SPLIT: 0 = never, 1 (default) = when the model gains at
+// least 15 % and the work is below 100 ms (beyond that the proof is bound by throughput and an imperfect split costs
+// more than the latencies it hides: measured, profiles/r02_lane_split_ab.txt), 2 = always.
+int lane_split_mode() {
+    static const int mode = [] { const char *e = getenv("B200MSM_LANE_SPLIT"); return e ? atoi(e) : 1; }();
+    return mode;
+}
+
+// B200MSM_TRACE=1: after every proof, the timeline of each lane on stderr (development; tools/lane_split_ab.sh)
+bool trace_on() {
+    static const bool on = [] { const char *e = getenv("B200MSM_TRACE"); return e && *e && *e != '0'; }();
+    return on;
+}
+void trace_lanes(b200msm_ctx *ctx, const b200msm_key *key) {
+    static const char *name[5] = {"A", "B1", "B2", "L", "H"};
+    cudaSetDevice(ctx->device);
+    for (int l = 0; l < NLANES; ++l) {
+        const Lane &ln = ctx->lanes[l];
+        if (!ln.timed) continue;
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        for (int e = 0; e < 6; ++e) cudaEventElapsedTime(&t[e], key->t0, ln.ev[e]);
+        fprintf(stderr, "[trace] shard %d lane %d %-2s sms %3d | start %7.2f sorted %7.2f accumulated %7.2f reduced %7.2f end %7.2f ms\n", key->shard, l, name[l],
+                ctx->lane_sms[l], t[0], t[2], t[3], t[4], t[5]);
+    }
+    if (key->shard == 0) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, key->t0, ctx->fft.ev[0]);
+        cudaEventElapsedTime(&b, key->t0, ctx->fft.ev[1]);
+        fprintf(stderr, "[trace] shard 0 compute_H | start %7.2f end %7.2f ms\n", a, b);
+    }
+}
+
+void lane_split_clear(b200msm_ctx *ctx) {
+    for (int l = 0; l < NLANES; ++l) ctx->lane_sms[l] = 0;
+}
+
+// cost[q]: query q alone on the whole GPU.  Returns true (and the SMs of each lane) when the queries should run side by side.
+bool lane_split_compute(const MsmCost cost[5], bool shard0, size_t d, int sm_count, int mode, int sms[5], double est_ns[2]) {
+    double W[5], L[5];
+    for (int q = 0; q < 5; ++q) { W[q] = cost[q].work_ns; L[q] = cost[q].latency_ns; sms[q] = 0; }
+    // compute_H before the H query: seven transforms of M = d + 1 points, (M / 2) log2 M butterflies each, and the
+    // pointwise passes, at the multiplier's 7.7 G products per second; three vectors of M elements cross PCIe first.
+    // Shard 0 runs them on lane 4's SMs (work of that party); the other shards wait for them (latency: about a
+    // third of shard 0's GPU is what the split gives them).
+    const double M = double(d + 1);
+    const double fft_w = 0.13 * (3.5 * log2(M > 2 ? M : 2) + 6.0) * M, fft_l = 3.0 * M * 96.0 / 40.0 + 150000.0;
+    double serial = 0;
+    for (int q = 0; q < 5; ++q) serial += W[q] + L[q];                 // one after the other on the whole GPU ...
+    if (shard0) serial += fft_w;                                       // ... the FFTs squeezed in between
+    if (W[4] > 0) {
+        if (shard0) { W[4] += fft_w; L[4] += fft_l; }
+        else L[4] += fft_l + 3.0 * fft_w;
+    }
+    double sumW = 0, lo = 0;
+    for (int q = 0; q < 5; ++q) { sumW += W[q]; if (W[q] > 0 && L[q] > lo) lo = L[q]; }
+    est_ns[0] = serial;
+    est_ns[1] = serial;
+    if (sumW <= 0 || mode <= 0) return false;
+    double hi = lo + sumW;                                            // every term W_q / (hi - L_q) <= W_q / sumW
+    for (int it = 0; it < 60; ++it) {
+        const double T = 0.5 * (lo + hi);
+        double f = 0;
+        for (int q = 0; q < 5; ++q) if (W[q] > 0) f += W[q] / (T - L[q]);
+        if (f > 1.0) lo = T; else hi = T;
+    }
+    const double T = hi;
+    est_ns[1] = T;
+    if (mode == 1 && !(T <= 0.85 * serial && sumW <= 100e6)) return false;
+    // whole SMs: a handful at least for lane 4 (the FFT launches are short and many), one for any other MSM, the
+    // rounding goes to (or comes from) the largest party
+    int total = 0, big = 0;
+    for (int q = 0; q < 5; ++q) {
+        if (W[q] <= 0) continue;
+        sms[q] = std::max(q == 4 ? std::min(8, std::max(1, sm_count / 8)) : 1, (int)(W[q] / (T - L[q]) * sm_count));
+        total += sms[q];
+        if (W[q] > W[big]) big = q;
+    }
+    while (total > sm_count && sms[big] > 1) { --sms[big]; --total; }
+    if (total < sm_count) sms[big] += sm_count - total;
+    return true;
+}
+
+void lane_split_plan(b200msm_ctx *ctx, const b200msm_key *key) {
+    lane_split_clear(ctx);
+    MsmCost cost[5];
+    for (int q = 0; q < 5; ++q) {
+        const BaseSet &bs = ctx->sets[key->slot[q]];
+        cost[q] = key->cnt[q] ? model_cost(key->cnt[q], degree_of(ctx->curve, bs.group), cfg_for_set(ctx, bs, key->cnt[q])) : MsmCost{0.0, 0.0};
+    }
+    int sms[5];
+    double est[2];
+    if (lane_split_compute(cost, key->shard == 0, key->d, ctx->sm_count, lane_split_mode(), sms, est))
+        for (int q = 0; q < 5; ++q) ctx->lane_sms[q] = sms[q];
+}
+
 // First half of a proof on one shard: its witness slice and r on its device, its four witness MSMs in flight.
 int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, const uint64_t *r, Partials &P) {
     int rc;
     // The witness crosses PCIe once; the B1 query runs on r * w so that its result is the r * Bt1 term of C directly
     // (sum (r w_i) B1_i = r * sum w_i B1_i: the same group element, no 753-step scalar multiplication afterwards).
     CU(cudaSetDevice(ctx->device));
+    CU(cudaEventRecord(key->t0, key->stream));
     CU(cudaMemcpyAsync(key->w_dev, w + key->w_lo * 12, key->w_cnt * 96, cudaMemcpyHostToDevice, key->stream));
     CU(cudaMemcpyAsync(key->r_dev, r, 96, cudaMemcpyHostToDevice, key->stream));
     const uint32_t *wa = key->w_dev + (key->lo[0] - key->w_lo) * 24;          // first witness element of the A / B1 / B2 slice
@@ -153,7 +287,8 @@ int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, con
     if ((rc = b200msm_internal_fr_scale(ctx, key->cnt[0], wa, key->r_dev, key->rw_dev, key->stream))) return rc;
     CU(cudaEventRecord(key->ready, key->stream));
     for (int l = 0; l < 4; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, key->ready, 0));
-    // the four witness MSMs in flight together (cuda_prover_piecewise.cu:162-167)
+    // the four witness MSMs in flight together (cuda_prover_piecewise.cu:162-167), side by side when the proof is small
+    lane_split_plan(ctx, key);
     if ((rc = b200msm_msm_async(ctx, 0, key->slot[0], 0, reinterpret_cast<const uint64_t *>(wa), key->cnt[0], P.A))) return rc;
     if ((rc = b200msm_msm_async(ctx, 1, key->slot[1], 0, reinterpret_cast<const uint64_t *>(key->rw_dev), key->cnt[1], P.rB1))) return rc;
     if ((rc = b200msm_msm_async(ctx, 2, key->slot[2], 0, reinterpret_cast<const uint64_t *>(wa), key->cnt[2], P.B2))) return rc;
@@ -161,8 +296,11 @@ int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, con
     return B200MSM_OK;
 }
 void prove_drain(b200msm_ctx *const *ctxs, int n) {
-    for (int g = 0; g < n; ++g)
-        for (int l = 0; l < 4; ++l) b200msm_wait(ctxs[g], l);
+    for (int g = 0; g < n; ++g) {
+        for (int l = 0; l < NLANES; ++l)
+            if (ctxs[g]->lanes[l].pending) b200msm_wait(ctxs[g], l);
+        lane_split_clear(ctxs[g]);
+    }
 }
 
 // Second half: the H polynomial on shard 0's GPU beside the MSMs, its coefficients handed to the other shards over
@@ -175,23 +313,26 @@ int prove_finish(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int n, cons
     const uint64_t *h_dev = nullptr;
     int rc = b200msm_compute_h(c0, d, ca, cb, cc, nullptr, &h_dev);
     for (int g = 0; g < n && !rc; ++g) {
-        rc = b200msm_wait(ctxs[g], 0);                    // lane 0 carries A, then H
-        if (rc) break;
         const uint64_t *hs = h_dev + keys[g]->lo[4] * 12;
         if (g > 0) {
-            // on lane 0's stream of the receiving GPU: ordered before the H query enqueued on the same stream below,
-            // and no device-wide synchronisation while lanes 1-3 are still working (the source is complete:
+            if (cudaSetDevice(ctxs[g]->device) != cudaSuccess) { rc = fail(c0, B200MSM_ERR_CUDA, "cannot select device %d", ctxs[g]->device); break; }
+            // on lane 4's stream of the receiving GPU: ordered before the H query enqueued on the same stream below,
+            // and no device-wide synchronisation while lanes 0-3 are still working (the source is complete:
             // b200msm_compute_h is synchronous)
-            if (cudaMemcpyPeerAsync(keys[g]->h_dev, ctxs[g]->device, hs, c0->device, keys[g]->cnt[4] * 96, ctxs[g]->lanes[0].stream) != cudaSuccess) {
+            if (cudaMemcpyPeerAsync(keys[g]->h_dev, ctxs[g]->device, hs, c0->device, keys[g]->cnt[4] * 96, ctxs[g]->lanes[4].stream) != cudaSuccess) {
                 rc = fail(c0, B200MSM_ERR_CUDA, "peer copy of the H coefficients to device %d failed", ctxs[g]->device);
                 break;
             }
             hs = reinterpret_cast<const uint64_t *>(keys[g]->h_dev);
         }
-        rc = b200msm_msm_async(ctxs[g], 0, keys[g]->slot[4], 0, hs, keys[g]->cnt[4], P[g].H);
+        rc = b200msm_msm_async(ctxs[g], 4, keys[g]->slot[4], 0, hs, keys[g]->cnt[4], P[g].H);   // beside the witness MSMs still running
     }
-    for (int g = 0; g < n; ++g)
-        for (int l = 0; l < 4; ++l) { const int rcw = b200msm_wait(ctxs[g], l); if (!rc) rc = rcw; }
+    for (int g = 0; g < n; ++g) {
+        for (int l = 0; l < NLANES; ++l)
+            if (ctxs[g]->lanes[l].pending) { const int rcw = b200msm_wait(ctxs[g], l); if (!rc) rc = rcw; }
+        if (!rc && trace_on()) trace_lanes(ctxs[g], keys[g]);
+        lane_split_clear(ctxs[g]);
+    }
     if (rc) return rc;
     // Fold the shards' partial points and normalise, all on shard 0's GPU: A = sum A_g, B = sum B2_g,
     // C = sum (H_g + L_g + r Bt1_g)  (:198-200) -- one upload of the 5 n partial points, three folds and three affine
@@ -240,6 +381,21 @@ int check_shards(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int n) {
     return B200MSM_OK;
 }
 }  // namespace
+
+// tests: the split b200msm_prove would choose for shard `shard` of `nshards` of a key with m variables and degree d (base sets
+// with the default table budget), from sizes alone -- pure host arithmetic.  ns[0] = modelled time of the five MSMs one after
+// the other, ns[1] = side by side.  Returns 1 when the lanes are split (sms[q] > 0), 0 when not.
+extern "C" int b200msm_internal_lane_split_model(int curve, size_t d, size_t m, int shard, int nshards, int sm_count, int mode, int sms[5], double ns[2]) {
+    const size_t count[5] = {m + 1, m + 1, m + 1, m >= 1 ? m - 1 : 0, d};
+    const int deg[5] = {1, 1, curve == B200MSM_MNT4753 ? 2 : 3, 1, 1};
+    MsmCost cost[5];
+    for (int q = 0; q < 5; ++q) {
+        size_t lo, cnt;
+        if (b200msm_shard_range(count[q], shard, nshards, &lo, &cnt)) return -1;
+        cost[q] = cnt ? model_cost(cnt, deg[q], choose_cfg(cnt, deg[q], 0, size_t(32) << 30, true)) : MsmCost{0.0, 0.0};
+    }
+    return lane_split_compute(cost, shard == 0, d, sm_count, mode, sms, ns) ? 1 : 0;
+}
 
 extern "C" {
 

@@ -40,6 +40,8 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
+    # hardware queues for the engine's streams (see b200msm_create); only effective before the process's first CUDA call
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     path = library_path()
     if not os.path.exists(path):
         raise ImportError("%s is missing: build it with `python -m gpu_groth16_prover_3x_b200.build` "
@@ -64,6 +66,7 @@ def load_library():
     lib.b200msm_shard_range.argtypes = [sz, ci, ci, ctypes.POINTER(sz), ctypes.POINTER(sz)]
     lib.b200msm_set_stream.argtypes = [vp, ci, vp]
     lib.b200msm_set_window_bits.argtypes = [vp, ci]
+    lib.b200msm_set_lane_sms.argtypes = [vp, ci, ci]
     lib.b200msm_set_table_budget.argtypes = [vp, sz]
     lib.b200msm_scalar_mul.argtypes = [vp, ci, vp, vp, vp]
     lib.b200msm_key_load.argtypes = [vp, vp, sz, ctypes.POINTER(vp)]
@@ -254,6 +257,10 @@ class MsmContext:
 
     def set_window_bits(self, c):
         self._check(self.lib.b200msm_set_window_bits(self._h, c))
+
+    def set_lane_sms(self, lane, sms):
+        """MSMs enqueued on `lane` afterwards occupy at most `sms` SMs (0: all), so that lanes run side by side."""
+        self._check(self.lib.b200msm_set_lane_sms(self._h, lane, sms))
 
     def last_timings(self, lane=0):
         ms = (ctypes.c_float * 6)()

@@ -68,7 +68,7 @@ int b200msm_bases_info(b200msm_ctx *ctx, int slot, uint64_t info[6]);
  * through the host adaptor in INTEGRATION.md, B::multiexp_G1 / multiexp_G2
  * (prover_reference_functions.cpp:350-368, 690-708).
  * `scalars_mont` may be host (pageable or pinned) or device memory; `out_xyz` is host memory.
- * The _async form enqueues on internal stream `lane` (0..3, the reference used one CUDA stream per
+ * The _async form enqueues on internal stream `lane` (0..4, the reference used one CUDA stream per
  * MSM as a future: cuda_prover_piecewise.cu:162-167,187-193) and returns immediately; the result
  * is valid after b200msm_wait(ctx, lane). */
 int b200msm_msm(b200msm_ctx *ctx, int slot, size_t offset, const uint64_t *scalars_mont, size_t n, uint64_t *out_xyz);
@@ -129,7 +129,8 @@ int b200msm_scalar_mul(b200msm_ctx *ctx, int group, const uint64_t *affine, cons
  * C = Ht + Lt + r * Bt1 and groth16_output_write.  `params_image` / `input_image` are the bytes of the reference's
  * <curve>-parameters and <curve>-input files (generate_parameters.cpp:59-108, main.cpp:35-85; host memory);
  * `proof` receives b200msm_proof_bytes() bytes, identical to the file the reference's provers write
- * (A || B || C affine: 768 bytes for MNT4753, 960 for MNT6753).  Single GPU; uses lanes 0-3 of the context. */
+ * (A || B || C affine: 768 bytes for MNT4753, 960 for MNT6753).  Single GPU; uses lanes 0-4 of the context
+ * (A, B1, B2, L, H). */
 typedef struct b200msm_key b200msm_key;
 int b200msm_key_load(b200msm_ctx *ctx, const void *params_image, size_t bytes, b200msm_key **key);
 int b200msm_key_load_file(b200msm_ctx *ctx, const char *path, b200msm_key **key);
@@ -162,6 +163,15 @@ void b200msm_pinned_free(void *p);
  * internal stream).  The reference hands a cudaStream_t& back to its caller for the same purpose
  * (reduce.cu:131-135): ordering the MSM against the caller's own work and timing it with events. */
 int b200msm_set_stream(b200msm_ctx *ctx, int lane, void *cuda_stream);
+
+/* MSMs enqueued on `lane` afterwards occupy at most `sms` SMs (0, or anything outside (0, SM count): all of them).
+ * The accumulation and the first reduction rounds of an MSM are persistent kernels of one block per SM; with the
+ * default every MSM takes the whole GPU and MSMs on different lanes run one after the other.  Small MSMs are bound by
+ * the LATENCY of their rounds, not by throughput: giving the lanes disjoint parts of the GPU lets them run side by
+ * side (b200msm_prove does this on its own for the four witness MSMs of a small proof, B200MSM_LANE_SPLIT=0 turns
+ * it off).  The result does not depend on the setting.  The reference has no counterpart: its four kernels shared
+ * the GPU through the hardware scheduler (cuda_prover_piecewise.cu:162-167). */
+int b200msm_set_lane_sms(b200msm_ctx *ctx, int lane, int sms);
 
 /* Tuning / introspection. */
 /* Window width for MSMs and for the tables of base sets uploaded afterwards; 0 = automatic.  An MSM

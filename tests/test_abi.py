@@ -73,3 +73,31 @@ def test_create_fails_loudly_without_gpu(engine_lib):
     assert e.value.code == 2
     h = ctypes.c_void_p()
     assert engine_lib.b200msm_create(7, 0, ctypes.byref(h)) == 1  # bad curve id
+
+
+def test_lane_split_model(engine_lib):
+    """The SM split b200msm_prove gives the five MSMs of a proof (csrc/prover.cu, pure host arithmetic): lanes get
+    disjoint parts of the GPU that add up to all of it for small proofs, the large ones (bound by throughput) are
+    left one after the other on the whole GPU, and the environment knob's modes 0 / 2 mean never / always."""
+    f = engine_lib.b200msm_internal_lane_split_model
+    f.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                  ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]
+
+    def plan(curve, log_d, shard=0, nshards=1, mode=1, sm=148):
+        sms, ns = (ctypes.c_int * 5)(), (ctypes.c_double * 2)()
+        on = f(curve, (1 << log_d) - 1, 1 << log_d, shard, nshards, sm, mode, sms, ns)
+        return on, list(sms), ns[0], ns[1]
+
+    for curve, log_d in ((1, 15), (0, 14), (1, 10), (0, 17)):        # default MNT6753, the two fast instances, a 2^17 shard
+        on, sms, serial, side = plan(curve, log_d)
+        assert on == 1 and sum(sms) == 148 and min(sms) >= 1 and side < 0.85 * serial
+        assert sms[2] == max(sms)                                     # the G2 query is the largest party
+        assert sms[0] == sms[1]                                       # A and B1: same size, same share
+    on, sms, serial, side = plan(0, 20)                               # default MNT4753 on one GPU: throughput-bound
+    assert on == 0 and sms == [0] * 5
+    assert plan(0, 20, mode=2)[0] == 1 and sum(plan(0, 20, mode=2)[1]) == 148
+    assert plan(1, 15, mode=0)[0] == 0
+    on, sms, _, _ = plan(0, 20, shard=0, nshards=8)                   # an eighth of it, with the FFTs on this GPU
+    assert on == 1 and sum(sms) == 148 and sms[4] >= 8
+    on, sms, _, _ = plan(1, 10, sm=16)                                # a small GPU: still whole SMs, still all of them
+    assert on == 1 and sum(sms) == 16 and min(sms) >= 1

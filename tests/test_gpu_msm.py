@@ -235,6 +235,43 @@ def test_async_lanes_and_shards(ctxs, oracle):
     ctx.free_bases(s2)
 
 
+def test_lanes_side_by_side(ctxs, oracle):
+    """b200msm_set_lane_sms: four MSMs on four lanes, each confined to its own part of the GPU (the split
+    b200msm_prove gives the witness MSMs of a small proof): the persistent grids and the number of shares change,
+    the results do not -- neither for generic scalars nor with giant buckets that are cut between shares."""
+    curve = 0
+    ctx = ctxs[curve]
+    n = 1 << 13
+    b1 = oracle.gen_bases(curve, 1, n)
+    b2 = oracle.gen_bases(curve, 2, n)
+    sc = po.gen_scalars(curve, n, 9)
+    skew = sc.copy().reshape(n, 12)
+    skew[: n // 2] = skew[0]                       # half of the points in the same bucket of every window
+    skew = skew.reshape(-1)
+    s1, s2 = ctx.upload_bases(1, b1), ctx.upload_bases(2, b2)
+    try:
+        want = [ctx.msm(s1, sc), ctx.msm(s2, sc), ctx.msm(s1, skew), ctx.msm(s2, skew)]
+        for split in ((20, 20, 60, 20), (1, 3, 7, 2), (0, 148, 1000, -1)):
+            for lane, sms in enumerate(split):
+                ctx.set_lane_sms(lane, sms)
+            ctx.msm_async(0, s1, sc)
+            ctx.msm_async(1, s2, sc)
+            ctx.msm_async(2, s1, skew)
+            ctx.msm_async(3, s2, skew)
+            got = [ctx.wait(i) for i in range(4)]
+            for i, (g, w) in enumerate(zip(got, want)):
+                grp = 1 if i in (0, 2) else 2
+                assert (affine(oracle, curve, grp, g) == affine(oracle, curve, grp, w)).all(), (split, i)
+        assert (affine(oracle, curve, 1, want[0]) == oracle.msm(curve, 1, b1, sc)[0]).all()
+        with pytest.raises(pkg.MsmError):
+            ctx.set_lane_sms(5, 10)
+    finally:
+        for lane in range(4):
+            ctx.set_lane_sms(lane, 0)
+        ctx.free_bases(s1)
+        ctx.free_bases(s2)
+
+
 def test_errors(ctxs):
     ctx = ctxs[0]
     with pytest.raises(pkg.MsmError):

@@ -109,6 +109,12 @@ def test_whole_proof_through_the_c_abi(fast_params, curve):
                          capture_output=True, text=True, timeout=900).stdout
     print(out)
     assert sha256(os.path.join(d, curve + "-output-cli")) == hashlib.sha256(want).hexdigest()
+    # the witness MSMs one after the other on the whole GPU (0) and side by side on disjoint SMs (2: always): same proof
+    for mode in ("0", "2"):
+        name = os.path.join(d, curve + "-output-cli-split" + mode)
+        subprocess.run([cli, curve, "compute", params, inp, name, "2"], check=True, capture_output=True, text=True, timeout=900,
+                       env=dict(os.environ, B200MSM_LANE_SPLIT=mode))
+        assert sha256(name) == hashlib.sha256(want).hexdigest(), mode
 
 
 @pytest.mark.parametrize("nshards", [2, 3])
