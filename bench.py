@@ -545,8 +545,17 @@ def proof_leg(size, gpus, device):
         elif os.path.exists(ref_out):
             rec["reference_cached"] = True
         ours = os.path.join(cache, "%s-output-b200-%dgpu" % (curve, gpus))
-        log = subprocess.run([cli, curve, "compute", prm, inp, ours, "3", str(gpus)], cwd=cache, check=True, capture_output=True,
-                             text=True, timeout=900).stdout
+        run = subprocess.run([cli, curve, "compute", prm, inp, ours, "3", str(gpus)], cwd=cache, check=True, capture_output=True,
+                             text=True, timeout=900, env=dict(os.environ, B200MSM_TRACE="1"))
+        log = run.stdout
+        # B200MSM_TRACE=1: the prover reports each query's timeline on shard 0's GPU (CUDA events, ms since the proof began
+        # on the device) and the SMs its lane was confined to (0 = the whole GPU); kept for the last proof
+        lanes = re.findall(r"\[trace\] shard 0 lane \d (\S+)\s+sms\s+(\d+) \| start\s+([0-9.]+) sorted\s+[0-9.]+ accumulated\s+([0-9.]+) reduced\s+[0-9.]+ end\s+([0-9.]+) ms", run.stderr)
+        hpoly = re.findall(r"\[trace\] shard 0 compute_H \| start\s+([0-9.]+) end\s+([0-9.]+) ms", run.stderr)
+        if lanes:
+            rec["device_timeline_shard0_ms"] = {q: {"sms": int(sm), "start": float(a), "accumulated": float(b), "end": float(c)} for q, sm, a, b, c in lanes[-5:]}
+            if hpoly:
+                rec["device_timeline_shard0_ms"]["compute_H"] = {"start": float(hpoly[-1][0]), "end": float(hpoly[-1][1])}
         times = [float(x) for x in re.findall(r"Total time from input to output: ([0-9.]+) ms", log)]
         total = re.findall(r"Total runtime \(incl. key load\): ([0-9.]+) ms", log)
         upload = re.findall(r"key load \+ window tables: ([0-9.]+) ms", log)

@@ -11,7 +11,15 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <new>
+#include <thread>
 #include <vector>
+
+#include <cerrno>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 
 #include "host_ctx.cuh"
 
@@ -35,6 +43,38 @@ const GroupOps &b200msm_internal_ops(int curve, int group);
 
 namespace {
 inline int g2_deg(const b200msm_ctx *ctx) { return ctx->curve == B200MSM_MNT4753 ? 2 : 3; }
+
+// Bytes [off, off + len) of an open file into dst.  A witness of 2^20 elements is 100 MB and the H coefficients three
+// times that: one thread copies out of the page cache at 6-7 GB/s (64 ms for the default MNT4753 input, more than
+// the five MSMs take on eight GPUs: profiles/r02_proof_8gpu_lane_trace.txt), so large ranges are cut into slices of
+// at least 8 MB read by up to eight threads with pread.
+constexpr double READ_BYTES_PER_NS = 10.0;     // what the planner of the lane split expects of it
+bool read_slice(int fd, char *dst, size_t off, size_t len) {
+    while (len) {
+        const ssize_t got = pread(fd, dst, len, (off_t)off);
+        if (got < 0 && errno == EINTR) continue;
+        if (got <= 0) return false;                       // error, or the file ends before the range does
+        dst += got; off += (size_t)got; len -= (size_t)got;
+    }
+    return true;
+}
+bool read_range(int fd, char *dst, size_t off, size_t len) {
+    const size_t min_slice = size_t(8) << 20;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t nt = std::min<size_t>(std::min<size_t>(8, hw), std::max<size_t>(1, len / min_slice));
+    if (nt <= 1) return read_slice(fd, dst, off, len);
+    std::vector<char> okv(nt, 0);
+    std::vector<std::thread> th;
+    const size_t per = ((len + nt - 1) / nt + 4095) & ~size_t(4095);
+    for (size_t t = 0; t < nt; ++t) {
+        const size_t lo = std::min(len, t * per), hi = std::min(len, lo + per);
+        th.emplace_back([=, &okv] { okv[t] = read_slice(fd, dst + lo, off + lo, hi - lo) ? 1 : 0; });
+    }
+    for (auto &x : th) x.join();
+    for (char o : okv) if (!o) return false;
+    return true;
+}
+
 
 // One pass over every kernel a proof launches, on zeros: a small MSM per query on its lane and, on shard 0, compute_H.
 // The CUDA runtime loads a kernel at its FIRST launch and that load waits for the kernels already running; with the
@@ -135,16 +175,15 @@ int b200msm_key_load(b200msm_ctx *ctx, const void *params_image, size_t bytes, b
 int b200msm_key_load_file(b200msm_ctx *ctx, const char *path, b200msm_key **out) {
     if (!ctx) return B200MSM_ERR_ARG;
     if (!path || !out) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
-    FILE *f = fopen(path, "rb");
-    if (!f) return fail(ctx, B200MSM_ERR_ARG, "cannot open %s", path);
-    fseek(f, 0, SEEK_END);
-    const long n = ftell(f);
-    fseek(f, 0, SEEK_SET);
-    std::vector<char> buf(n > 0 ? (size_t)n : 0);
-    const bool ok = n > 0 && fread(buf.data(), 1, (size_t)n, f) == (size_t)n;
-    fclose(f);
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(ctx, B200MSM_ERR_ARG, "cannot open %s", path);
+    struct stat st;
+    const size_t n = fstat(fd, &st) == 0 && st.st_size > 0 ? (size_t)st.st_size : 0;
+    std::unique_ptr<char[]> buf(n ? new (std::nothrow) char[n] : nullptr);     // not zeroed: 1.4 GB for the default MNT4753 key
+    const bool ok = buf && read_range(fd, buf.get(), 0, n);
+    close(fd);
     if (!ok) return fail(ctx, B200MSM_ERR_ARG, "cannot read %s", path);
-    return b200msm_key_load(ctx, buf.data(), buf.size(), out);
+    return b200msm_key_load(ctx, buf.get(), n, out);
 }
 
 int b200msm_key_info(const b200msm_key *key, uint64_t info[2]) {
@@ -214,8 +253,10 @@ void lane_split_clear(b200msm_ctx *ctx) {
     for (int l = 0; l < NLANES; ++l) ctx->lane_sms[l] = 0;
 }
 
-// cost[q]: query q alone on the whole GPU.  Returns true (and the SMs of each lane) when the queries should run side by side.
-bool lane_split_compute(const MsmCost cost[5], bool shard0, size_t d, int sm_count, int mode, int sms[5], double est_ns[2]) {
+// cost[q]: query q alone on the whole GPU; fft_delay_ns: how long after the witness MSMs the FFTs of compute_H can start
+// (b200msm_prove_sharded_file reads their input, three quarters of the file, while the witness MSMs run).  Returns
+// true (and the SMs of each lane) when the queries should run side by side.
+bool lane_split_compute(const MsmCost cost[5], bool shard0, size_t d, double fft_delay_ns, int sm_count, int mode, int sms[5], double est_ns[2]) {
     double W[5], L[5];
     for (int q = 0; q < 5; ++q) { W[q] = cost[q].work_ns; L[q] = cost[q].latency_ns; sms[q] = 0; }
     // compute_H before the H query: seven transforms of M = d + 1 points, (M / 2) log2 M butterflies each, and the
@@ -225,11 +266,12 @@ bool lane_split_compute(const MsmCost cost[5], bool shard0, size_t d, int sm_cou
     const double M = double(d + 1);
     const double fft_w = 0.13 * (3.5 * log2(M > 2 ? M : 2) + 6.0) * M, fft_l = 3.0 * M * 96.0 / 40.0 + 150000.0;
     double serial = 0;
-    for (int q = 0; q < 5; ++q) serial += W[q] + L[q];                 // one after the other on the whole GPU ...
-    if (shard0) serial += fft_w;                                       // ... the FFTs squeezed in between
+    for (int q = 0; q < 4; ++q) serial += W[q] + L[q];                 // one after the other on the whole GPU ...
+    if (shard0) serial += fft_w;                                       // ... the FFTs squeezed in between, or after their input has arrived
+    serial = std::max(serial, fft_delay_ns + fft_l + fft_w) + W[4] + L[4];
     if (W[4] > 0) {
-        if (shard0) { W[4] += fft_w; L[4] += fft_l; }
-        else L[4] += fft_l + 3.0 * fft_w;
+        if (shard0) { W[4] += fft_w; L[4] += fft_delay_ns + fft_l; }
+        else L[4] += fft_delay_ns + fft_l + 3.0 * fft_w;
     }
     double sumW = 0, lo = 0;
     for (int q = 0; q < 5; ++q) { sumW += W[q]; if (W[q] > 0 && L[q] > lo) lo = L[q]; }
@@ -260,7 +302,7 @@ bool lane_split_compute(const MsmCost cost[5], bool shard0, size_t d, int sm_cou
     return true;
 }
 
-void lane_split_plan(b200msm_ctx *ctx, const b200msm_key *key) {
+void lane_split_plan(b200msm_ctx *ctx, const b200msm_key *key, double fft_delay_ns) {
     lane_split_clear(ctx);
     MsmCost cost[5];
     for (int q = 0; q < 5; ++q) {
@@ -269,12 +311,12 @@ void lane_split_plan(b200msm_ctx *ctx, const b200msm_key *key) {
     }
     int sms[5];
     double est[2];
-    if (lane_split_compute(cost, key->shard == 0, key->d, ctx->sm_count, lane_split_mode(), sms, est))
+    if (lane_split_compute(cost, key->shard == 0, key->d, fft_delay_ns, ctx->sm_count, lane_split_mode(), sms, est))
         for (int q = 0; q < 5; ++q) ctx->lane_sms[q] = sms[q];
 }
 
 // First half of a proof on one shard: its witness slice and r on its device, its four witness MSMs in flight.
-int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, const uint64_t *r, Partials &P) {
+int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, const uint64_t *r, double fft_delay_ns, Partials &P) {
     int rc;
     // The witness crosses PCIe once; the B1 query runs on r * w so that its result is the r * Bt1 term of C directly
     // (sum (r w_i) B1_i = r * sum w_i B1_i: the same group element, no 753-step scalar multiplication afterwards).
@@ -288,7 +330,7 @@ int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, con
     CU(cudaEventRecord(key->ready, key->stream));
     for (int l = 0; l < 4; ++l) CU(cudaStreamWaitEvent(ctx->lanes[l].stream, key->ready, 0));
     // the four witness MSMs in flight together (cuda_prover_piecewise.cu:162-167), side by side when the proof is small
-    lane_split_plan(ctx, key);
+    lane_split_plan(ctx, key, fft_delay_ns);
     if ((rc = b200msm_msm_async(ctx, 0, key->slot[0], 0, reinterpret_cast<const uint64_t *>(wa), key->cnt[0], P.A))) return rc;
     if ((rc = b200msm_msm_async(ctx, 1, key->slot[1], 0, reinterpret_cast<const uint64_t *>(key->rw_dev), key->cnt[1], P.rB1))) return rc;
     if ((rc = b200msm_msm_async(ctx, 2, key->slot[2], 0, reinterpret_cast<const uint64_t *>(wa), key->cnt[2], P.B2))) return rc;
@@ -385,7 +427,8 @@ int check_shards(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int n) {
 // tests: the split b200msm_prove would choose for shard `shard` of `nshards` of a key with m variables and degree d (base sets
 // with the default table budget), from sizes alone -- pure host arithmetic.  ns[0] = modelled time of the five MSMs one after
 // the other, ns[1] = side by side.  Returns 1 when the lanes are split (sms[q] > 0), 0 when not.
-extern "C" int b200msm_internal_lane_split_model(int curve, size_t d, size_t m, int shard, int nshards, int sm_count, int mode, int sms[5], double ns[2]) {
+extern "C" int b200msm_internal_lane_split_model(int curve, size_t d, size_t m, int shard, int nshards, double fft_delay_ns, int sm_count, int mode, int sms[5],
+                                                 double ns[2]) {
     const size_t count[5] = {m + 1, m + 1, m + 1, m >= 1 ? m - 1 : 0, d};
     const int deg[5] = {1, 1, curve == B200MSM_MNT4753 ? 2 : 3, 1, 1};
     MsmCost cost[5];
@@ -394,7 +437,16 @@ extern "C" int b200msm_internal_lane_split_model(int curve, size_t d, size_t m, 
         if (b200msm_shard_range(count[q], shard, nshards, &lo, &cnt)) return -1;
         cost[q] = cnt ? model_cost(cnt, deg[q], choose_cfg(cnt, deg[q], 0, size_t(32) << 30, true)) : MsmCost{0.0, 0.0};
     }
-    return lane_split_compute(cost, shard == 0, d, sm_count, mode, sms, ns) ? 1 : 0;
+    return lane_split_compute(cost, shard == 0, d, fft_delay_ns, sm_count, mode, sms, ns) ? 1 : 0;
+}
+
+// tests: the parallel file reader on its own (no GPU involved)
+extern "C" int b200msm_internal_read_range(const char *path, size_t off, size_t len, void *dst) {
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return -1;
+    const bool ok = read_range(fd, static_cast<char *>(dst), off, len);
+    close(fd);
+    return ok ? 0 : 1;
 }
 
 extern "C" {
@@ -409,7 +461,7 @@ int b200msm_prove_sharded(b200msm_ctx *const *ctxs, b200msm_key *const *keys, in
     const uint64_t *w = static_cast<const uint64_t *>(input_image);
     const uint64_t *ca = w + (m + 1) * 12, *cb = ca + (d + 1) * 12, *cc = cb + (d + 1) * 12, *r = cc + (d + 1) * 12;
     std::vector<Partials> P((size_t)n);
-    for (int g = 0; g < n && !rc; ++g) rc = prove_begin(ctxs[g], keys[g], w, r, P[g]);
+    for (int g = 0; g < n && !rc; ++g) rc = prove_begin(ctxs[g], keys[g], w, r, 0.0, P[g]);
     if (rc) { prove_drain(ctxs, n); return rc; }
     return prove_finish(ctxs, keys, n, ca, cb, cc, P.data(), proof);
 }
@@ -424,20 +476,21 @@ int b200msm_prove_sharded_file(b200msm_ctx *const *ctxs, b200msm_key *const *key
     b200msm_ctx *ctx = ctxs[0];
     if (!input_path || !buffer || !proof) return fail(ctx, B200MSM_ERR_ARG, "null pointer");
     const size_t d = keys[0]->d, m = keys[0]->m, bytes = b200msm_input_bytes(keys[0]);
-    FILE *f = fopen(input_path, "rb");
-    if (!f) return fail(ctx, B200MSM_ERR_ARG, "cannot open %s", input_path);
+    const int fd = open(input_path, O_RDONLY);
+    if (fd < 0) return fail(ctx, B200MSM_ERR_ARG, "cannot open %s", input_path);
     char *img = static_cast<char *>(buffer);
     const size_t w_bytes = (m + 1) * 96, h_bytes = 3 * (d + 1) * 96;
-    bool ok = fseek(f, 0, SEEK_END) == 0 && (size_t)ftell(f) == bytes;
-    ok = ok && fseek(f, (long)(bytes - 96), SEEK_SET) == 0 && fread(img + bytes - 96, 1, 96, f) == 96;
-    ok = ok && fseek(f, 0, SEEK_SET) == 0 && fread(img, 1, w_bytes, f) == w_bytes;
-    if (!ok) { fclose(f); return fail(ctx, B200MSM_ERR_ARG, "%s is not an input file of %zu bytes for this key", input_path, bytes); }
+    struct stat st;
+    bool ok = fstat(fd, &st) == 0 && (size_t)st.st_size == bytes;
+    ok = ok && read_range(fd, img + bytes - 96, bytes - 96, 96) && read_range(fd, img, 0, w_bytes);
+    if (!ok) { close(fd); return fail(ctx, B200MSM_ERR_ARG, "%s is not an input file of %zu bytes for this key", input_path, bytes); }
     uint64_t *w = reinterpret_cast<uint64_t *>(img);
     const uint64_t *ca = w + (m + 1) * 12, *cb = ca + (d + 1) * 12, *cc = cb + (d + 1) * 12, *r = cc + (d + 1) * 12;
     std::vector<Partials> P((size_t)n);
-    for (int g = 0; g < n && !rc; ++g) rc = prove_begin(ctxs[g], keys[g], w, r, P[g]);
-    if (!rc && fread(img + w_bytes, 1, h_bytes, f) != h_bytes) rc = fail(ctx, B200MSM_ERR_ARG, "short read of %s", input_path);
-    fclose(f);
+    const double read_ns = double(h_bytes) / READ_BYTES_PER_NS;           // the FFTs cannot start before their input is here
+    for (int g = 0; g < n && !rc; ++g) rc = prove_begin(ctxs[g], keys[g], w, r, read_ns, P[g]);
+    if (!rc && !read_range(fd, img + w_bytes, w_bytes, h_bytes)) rc = fail(ctx, B200MSM_ERR_ARG, "short read of %s", input_path);
+    close(fd);
     if (rc) { prove_drain(ctxs, n); return rc; }
     return prove_finish(ctxs, keys, n, ca, cb, cc, P.data(), proof);
 }

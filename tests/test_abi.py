@@ -80,12 +80,12 @@ def test_lane_split_model(engine_lib):
     disjoint parts of the GPU that add up to all of it for small proofs, the large ones (bound by throughput) are
     left one after the other on the whole GPU, and the environment knob's modes 0 / 2 mean never / always."""
     f = engine_lib.b200msm_internal_lane_split_model
-    f.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    f.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_int, ctypes.c_int,
                   ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_double)]
 
-    def plan(curve, log_d, shard=0, nshards=1, mode=1, sm=148):
+    def plan(curve, log_d, shard=0, nshards=1, mode=1, sm=148, delay_ms=0.0):
         sms, ns = (ctypes.c_int * 5)(), (ctypes.c_double * 2)()
-        on = f(curve, (1 << log_d) - 1, 1 << log_d, shard, nshards, sm, mode, sms, ns)
+        on = f(curve, (1 << log_d) - 1, 1 << log_d, shard, nshards, delay_ms * 1e6, sm, mode, sms, ns)
         return on, list(sms), ns[0], ns[1]
 
     for curve, log_d in ((1, 15), (0, 14), (1, 10), (0, 17)):        # default MNT6753, the two fast instances, a 2^17 shard
@@ -99,5 +99,29 @@ def test_lane_split_model(engine_lib):
     assert plan(1, 15, mode=0)[0] == 0
     on, sms, _, _ = plan(0, 20, shard=0, nshards=8)                   # an eighth of it, with the FFTs on this GPU
     assert on == 1 and sum(sms) == 148 and sms[4] >= 8
+    # ... but not when the FFTs' input (300 MB of the input file) arrives 30 ms into the proof: file read -> FFTs -> H
+    # query is then the critical path and wants the whole GPU (measured: profiles/r02_proof_8gpu_lane_trace.txt)
+    assert plan(0, 20, shard=0, nshards=8, delay_ms=30.0)[0] == 0
+    assert plan(1, 15, delay_ms=0.9)[0] == 1                          # 9.4 MB: no matter
     on, sms, _, _ = plan(1, 10, sm=16)                                # a small GPU: still whole SMs, still all of them
     assert on == 1 and sum(sms) == 16 and min(sms) >= 1
+
+
+def test_parallel_file_reader(engine_lib, tmp_path):
+    """The input / key file reader of the prover (csrc/prover.cu read_range: slices of at least 8 MB read by up to
+    eight threads with pread): every range comes back byte for byte, ranges beyond the end of the file fail."""
+    import numpy as np
+    f = engine_lib.b200msm_internal_read_range
+    f.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p]
+    n = (70 << 20) + 12345
+    data = np.random.default_rng(5).integers(0, 256, n, dtype=np.uint8)
+    path = tmp_path / "blob"
+    data.tofile(path)
+    for off, ln in ((0, n), (0, 96), (n - 96, 96), (4097, (64 << 20) + 5), (1 << 20, 17 << 20), (123, 0), (9, (8 << 20) - 1)):
+        out = np.full(ln + 8, 0xAB, np.uint8)
+        assert f(str(path).encode(), off, ln, out.ctypes.data) == 0, (off, ln)
+        assert (out[:ln] == data[off:off + ln]).all() and (out[ln:] == 0xAB).all(), (off, ln)
+    out = np.zeros(32 << 20, np.uint8)
+    assert f(str(path).encode(), n - 100, 200, out.ctypes.data) == 1                 # short file, single slice
+    assert f(str(path).encode(), n - (20 << 20), 32 << 20, out.ctypes.data) == 1     # short file, several slices
+    assert f(b"/nonexistent/blob", 0, 1, out.ctypes.data) == -1
