@@ -5,8 +5,8 @@ The compute path is hand-written CUDA for sm_100a behind the C ABI of include/b2
 (csrc/msm.cu -> libb200msm.so).  This package is the thin host mirror of that ABI; it has no CPU
 fallback and raises if the CUDA library is missing.
 """
-from .engine import (G1, G2, MNT4753, MNT6753, MsmContext, MsmError, degree, library_path, load_library,
-                     prove_sharded, shard_ranges)
+from .engine import (G1, G2, MNT4753, MNT6753, MsmContext, MsmError, degree, library_path, load_key_sharded_file,
+                     load_library, prove_sharded, shard_ranges)
 
-__all__ = ["G1", "G2", "MNT4753", "MNT6753", "MsmContext", "MsmError", "degree", "library_path", "load_library",
-           "prove_sharded", "shard_ranges"]
+__all__ = ["G1", "G2", "MNT4753", "MNT6753", "MsmContext", "MsmError", "degree", "library_path", "load_key_sharded_file",
+           "load_library", "prove_sharded", "shard_ranges"]

@@ -1,13 +1,12 @@
 // b200_prove -- command-line twin of the reference's GPU prover for its `compute` mode
 // (cuda_prover_piecewise.cu:232-263):   b200_prove <MNT4753|MNT6753> compute <params> <input> <output> [repeats [gpus]]
-// No preprocessing file and no libff: the parameter file is loaded into HBM once (b200msm_key_load_file), every
-// proof is one b200msm_prove call, the output file holds the same bytes as the reference provers write.
+// No preprocessing file and no libff: the parameter file is loaded into HBM once (b200msm_key_load_sharded_file), every
+// proof is one b200msm_prove_sharded_file call, the output file holds the same bytes as the reference provers write.
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/b200_msm.h"
@@ -35,27 +34,8 @@ int main(int argc, char **argv) {
         if (b200msm_create(curve_id, g, &ctxs[g])) { fprintf(stderr, "no usable sm_100 device %d\n", g); return 3; }
     b200msm_ctx *ctx = ctxs[0];
     auto t = std::chrono::high_resolution_clock::now();
-    if (gpus == 1) {
-        if (b200msm_key_load_file(ctx, argv[3], &keys[0])) { fprintf(stderr, "%s\n", b200msm_last_error(ctx)); return 2; }
-    } else {   // every GPU takes its point range of every query out of one image of the parameter file
-        FILE *pf = fopen(argv[3], "rb");
-        if (!pf) { fprintf(stderr, "cannot open %s\n", argv[3]); return 2; }
-        fseek(pf, 0, SEEK_END);
-        const long pn = ftell(pf);
-        fseek(pf, 0, SEEK_SET);
-        std::vector<char> image(pn > 0 ? (size_t)pn : 0);
-        const bool ok = pn > 0 && fread(image.data(), 1, (size_t)pn, pf) == (size_t)pn;
-        fclose(pf);
-        if (!ok) { fprintf(stderr, "cannot read %s\n", argv[3]); return 2; }
-        // one host thread per GPU: uploads and window-table builds of the shards run side by side
-        std::vector<int> rcs(gpus, 0);
-        std::vector<std::thread> loaders;
-        for (int g = 0; g < gpus; ++g)
-            loaders.emplace_back([&, g] { rcs[g] = b200msm_key_load_shard(ctxs[g], image.data(), image.size(), g, gpus, &keys[g]); });
-        for (auto &th : loaders) th.join();
-        for (int g = 0; g < gpus; ++g)
-            if (rcs[g]) { fprintf(stderr, "%s\n", b200msm_last_error(ctxs[g])); return 2; }
-    }
+    // every GPU takes its point range of every query out of one image of the parameter file, loaded by its own host thread
+    if (b200msm_key_load_sharded_file(ctxs.data(), gpus, argv[3], keys.data())) { fprintf(stderr, "%s\n", b200msm_last_error(ctx)); return 2; }
     b200msm_key *key = keys[0];
     uint64_t info[2];
     b200msm_key_info(key, info);

@@ -81,6 +81,7 @@ def load_library():
     lib.b200msm_prove.argtypes = [vp, vp, vp, sz, vp]
     lib.b200msm_prove_file.argtypes = [vp, vp, ctypes.c_char_p, vp, vp]
     lib.b200msm_key_load_shard.argtypes = [vp, vp, sz, ci, ci, ctypes.POINTER(vp)]
+    lib.b200msm_key_load_sharded_file.argtypes = [ctypes.POINTER(vp), ci, ctypes.c_char_p, ctypes.POINTER(vp)]
     lib.b200msm_prove_sharded.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ci, vp, sz, vp]
     lib.b200msm_prove_sharded_file.argtypes = [ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ctypes.c_char_p, vp, vp]
     lib.b200msm_pinned_alloc.argtypes = [sz]
@@ -374,6 +375,17 @@ class MsmContext:
             flags = np.ascontiguousarray(flags, dtype=np.uint32)
         self._check(self.lib.b200msm_selftest_point(self._h, group, op, n, acc.ctypes.data, _ptr(q), _ptr(flags), out.ctypes.data))
         return out
+
+
+def load_key_sharded_file(ctxs, path):
+    """All shards of a <curve>-parameters file, shard g into ctxs[g] (one host thread per GPU):
+    b200msm_key_load_sharded_file.  -> list of key handles, to be freed with ctxs[g].free_key(keys[g])."""
+    n = len(ctxs)
+    lib = ctxs[0].lib
+    ca = (ctypes.c_void_p * n)(*[c._h for c in ctxs])
+    ka = (ctypes.c_void_p * n)()
+    ctxs[0]._check(lib.b200msm_key_load_sharded_file(ca, n, path.encode(), ka))
+    return [ctypes.c_void_p(ka[g]) for g in range(n)]
 
 
 def prove_sharded(ctxs, keys, input_image):

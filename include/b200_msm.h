@@ -150,6 +150,9 @@ int b200msm_prove_file(b200msm_ctx *ctx, const b200msm_key *key, const char *inp
  * peer copy, the 5 n partial points are folded on shard 0's GPU.  No collective; ctxs[g] / keys[g] must be shard g of n
  * of the same parameter image.  Contexts may share a device (tests). */
 int b200msm_key_load_shard(b200msm_ctx *ctx, const void *params_image, size_t bytes, int shard, int nshards, b200msm_key **key);
+/* All shards from the <curve>-parameters FILE: read once, shard g loaded into ctxs[g] by its own host thread (uploads and
+ * window-table builds of the GPUs run side by side).  keys: nshards entries; on failure none is left allocated. */
+int b200msm_key_load_sharded_file(b200msm_ctx *const *ctxs, int nshards, const char *path, b200msm_key **keys);
 int b200msm_prove_sharded(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int nshards, const void *input_image, size_t bytes,
                           uint8_t *proof);
 int b200msm_prove_sharded_file(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int nshards, const char *input_path, void *buffer,

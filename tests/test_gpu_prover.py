@@ -142,6 +142,13 @@ def test_sharded_proof_through_the_c_abi(fast_params, nshards):
                 pkg.prove_sharded(ctxs[::-1], keys[::-1], open(inp, "rb").read())   # shards out of order
             for c, k in zip(ctxs, keys):
                 c.free_key(k)
+            # the same shards straight from the parameter FILE (b200msm_key_load_sharded_file: one host thread per shard)
+            keys = pkg.load_key_sharded_file(ctxs, params)
+            assert pkg.prove_sharded(ctxs, keys, open(inp, "rb").read()) == want
+            for c, k in zip(ctxs, keys):
+                c.free_key(k)
+            with pytest.raises(pkg.MsmError):
+                pkg.load_key_sharded_file(ctxs, inp)                                  # not a parameter file
         finally:
             for c in ctxs:
                 c.close()
