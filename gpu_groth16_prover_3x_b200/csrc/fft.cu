@@ -27,6 +27,7 @@ int fft_prepare(b200msm_ctx *ctx, int logm) {
     }
     if (f.logm == logm) return B200MSM_OK;
     fft_free(f);
+    f.staged = 0;
     CU(cudaFuncSetAttribute(k_ntt_tile<M, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << NTT_TILE_BITS));
     CU(cudaFuncSetAttribute(k_ntt_tile<M, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << NTT_TILE_BITS));
     const size_t m = size_t(1) << logm, EB = NLIMB * 4;
@@ -89,29 +90,54 @@ void fft_dit(const FftState &f, uint32_t *x, uint32_t m, int logm) {    // bit-r
     for (uint32_t len = 2; len <= m && len; len <<= 1) k_ntt_dit<M><<<(m / 2 + 127) / 128, 128, 0, f.stream>>>(x, f.tw, m, len);
 }
 
+// compute_H in two kinds of steps on the FFT stream, so that a caller whose three input vectors arrive one after the
+// other (b200msm_prove_sharded_file reads them from the input file) can have each one uploaded and transformed while
+// the next is still on its way:
+//   stage(which, src)   vector `which` (0 = ca, 1 = cb, 2 = cc) -> the context's work vector, then its coset evaluation:
+//                       inverse FFT, multiplication by the coset powers, forward FFT.  Asynchronous.
+//   finish()            (a * b - c) / Z pointwise, inverse FFT, coset scaling; waits for the result.
 template <class M>
-int compute_h_impl(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out_host,
-                   const uint64_t **out_dev) {
+int compute_h_check(b200msm_ctx *ctx, size_t d, int &logm) {
     const size_t m = d + 1;
-    int logm = 0;
+    logm = 0;
     while ((size_t(1) << logm) < m) ++logm;
     if ((size_t(1) << logm) != m || logm > M::TWO_ADICITY || logm > 30)
         return fail(ctx, B200MSM_ERR_ARG, "d + 1 = %zu is not a power of two within the field's 2-adicity (2^%d)", m, M::TWO_ADICITY);
-    int rc = fft_prepare<M>(ctx, logm);
+    return fft_prepare<M>(ctx, logm);
+}
+
+template <class M>
+int compute_h_stage(b200msm_ctx *ctx, size_t d, int which, const uint64_t *src) {
+    int logm;
+    int rc = compute_h_check<M>(ctx, d, logm);
     if (rc) return rc;
     FftState &f = ctx->fft;
+    if (which < 0 || which > 2 || (f.staged & (1u << which))) return fail(ctx, B200MSM_ERR_ARG, "compute_H: vector %d out of order", which);
     cudaStream_t st = f.stream;
-    const size_t bytes = m * NLIMB * 4;
+    const size_t m = d + 1;
+    const unsigned gm = (unsigned)((m + 127) / 128);
+    if (f.staged == 0) CU(cudaEventRecord(f.ev[0], st));
+    uint32_t *x = which == 0 ? f.a : (which == 1 ? f.b : f.c);
+    CU(cudaMemcpyAsync(x, src, m * NLIMB * 4, cudaMemcpyDefault, st));
+    ifft_dif<M>(f, x, (uint32_t)m, logm);                         // coset evaluation of the vector
+    k_pointwise_mul<M><<<gm, 128, 0, st>>>(x, f.cg_br, (uint32_t)m);
+    fft_dit<M>(f, x, (uint32_t)m, logm);
+    CU(cudaGetLastError());
+    f.staged |= 1u << which;
+    return B200MSM_OK;
+}
+
+template <class M>
+int compute_h_finish(b200msm_ctx *ctx, size_t d, uint64_t *out_host, const uint64_t **out_dev) {
+    int logm;
+    int rc = compute_h_check<M>(ctx, d, logm);
+    if (rc) return rc;
+    FftState &f = ctx->fft;
+    if (f.staged != 7u) { f.staged = 0; return fail(ctx, B200MSM_ERR_ARG, "compute_H: not all three vectors were staged"); }
+    f.staged = 0;
+    cudaStream_t st = f.stream;
+    const size_t m = d + 1;
     const unsigned gm = (unsigned)((m + 127) / 128), gm1 = (unsigned)((m + 1 + 127) / 128);
-    CU(cudaEventRecord(f.ev[0], st));
-    CU(cudaMemcpyAsync(f.a, ca, bytes, cudaMemcpyDefault, st));
-    CU(cudaMemcpyAsync(f.b, cb, bytes, cudaMemcpyDefault, st));
-    CU(cudaMemcpyAsync(f.c, cc, bytes, cudaMemcpyDefault, st));
-    for (uint32_t *x : {f.a, f.b, f.c}) {                       // coset evaluation of each of A, B, C
-        ifft_dif<M>(f, x, (uint32_t)m, logm);
-        k_pointwise_mul<M><<<gm, 128, 0, st>>>(x, f.cg_br, (uint32_t)m);
-        fft_dit<M>(f, x, (uint32_t)m, logm);
-    }
     k_h_pointwise<M><<<gm, 128, 0, st>>>(f.a, f.b, f.c, f.consts + FC_Z_INV * NLIMB, (uint32_t)m);
     ifft_dif<M>(f, f.a, (uint32_t)m, logm);
     k_h_final<M><<<gm1, 128, 0, st>>>(f.out, f.a, f.cgi_br, (uint32_t)m, logm);
@@ -122,6 +148,17 @@ int compute_h_impl(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_
     CU(cudaEventElapsedTime(&f.last_ms, f.ev[0], f.ev[1]));
     if (out_dev) *out_dev = reinterpret_cast<const uint64_t *>(f.out);
     return B200MSM_OK;
+}
+
+template <class M>
+int compute_h_impl(b200msm_ctx *ctx, size_t d, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc, uint64_t *out_host,
+                   const uint64_t **out_dev) {
+    ctx->fft.staged = 0;
+    int rc = compute_h_stage<M>(ctx, d, 0, ca);
+    if (!rc) rc = compute_h_stage<M>(ctx, d, 1, cb);
+    if (!rc) rc = compute_h_stage<M>(ctx, d, 2, cc);
+    if (rc) { ctx->fft.staged = 0; return rc; }
+    return compute_h_finish<M>(ctx, d, out_host, out_dev);
 }
 
 }  // namespace
@@ -143,6 +180,26 @@ int b200msm_internal_fft_prepare(b200msm_ctx *ctx, size_t d) {
     CU(cudaSetDevice(ctx->device));
     if (ctx->curve == B200MSM_MNT4753) return logm <= ModB::TWO_ADICITY ? fft_prepare<ModB>(ctx, logm) : fail(ctx, B200MSM_ERR_ARG, "domain too large");
     return logm <= ModA::TWO_ADICITY ? fft_prepare<ModA>(ctx, logm) : fail(ctx, B200MSM_ERR_ARG, "domain too large");
+}
+
+// internal (prover.cu): compute_H fed one vector at a time, see compute_h_stage above.  The scalar field of a curve is the
+// base field of the other one.
+int b200msm_internal_compute_h_stage(b200msm_ctx *ctx, size_t d, int which, const uint64_t *src) {
+    if (!ctx || !src) return B200MSM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    return ctx->curve == B200MSM_MNT4753 ? compute_h_stage<ModB>(ctx, d, which, src) : compute_h_stage<ModA>(ctx, d, which, src);
+}
+int b200msm_internal_compute_h_finish(b200msm_ctx *ctx, size_t d, const uint64_t **out_dev) {
+    if (!ctx || !out_dev) return B200MSM_ERR_ARG;
+    CU(cudaSetDevice(ctx->device));
+    return ctx->curve == B200MSM_MNT4753 ? compute_h_finish<ModB>(ctx, d, nullptr, out_dev) : compute_h_finish<ModA>(ctx, d, nullptr, out_dev);
+}
+// forget staged vectors and wait for whatever the FFT stream still reads from host memory (error paths)
+void b200msm_internal_compute_h_abort(b200msm_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    ctx->fft.staged = 0;
+    if (ctx->fft.stream) cudaStreamSynchronize(ctx->fft.stream);
 }
 
 extern "C" {

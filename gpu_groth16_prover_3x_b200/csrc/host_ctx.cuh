@@ -73,6 +73,7 @@ struct FftState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {};
     float last_ms = 0.f, tables_ms = 0.f;
+    unsigned staged = 0;     // bit v: input vector v of the compute_H in progress is uploaded and transformed (fft.cu)
 };
 
 // Scratch of the small host-facing routines (fold of partial points, affine normalisation, proof assembly): one

@@ -40,6 +40,9 @@ struct b200msm_key {
 int b200msm_internal_fr_scale(b200msm_ctx *ctx, size_t n, const uint32_t *in_dev, const uint32_t *k_dev, uint32_t *out_dev, cudaStream_t st);
 extern "C" int b200msm_internal_reserve(b200msm_ctx *ctx, int lane, int slot, size_t n);
 int b200msm_internal_fft_prepare(b200msm_ctx *ctx, size_t d);
+int b200msm_internal_compute_h_stage(b200msm_ctx *ctx, size_t d, int which, const uint64_t *src);
+int b200msm_internal_compute_h_finish(b200msm_ctx *ctx, size_t d, const uint64_t **out_dev);
+void b200msm_internal_compute_h_abort(b200msm_ctx *ctx);
 const GroupOps &b200msm_internal_ops(int curve, int group);
 
 namespace {
@@ -369,6 +372,7 @@ int prove_begin(b200msm_ctx *ctx, const b200msm_key *key, const uint64_t *w, con
     return B200MSM_OK;
 }
 void prove_drain(b200msm_ctx *const *ctxs, int n) {
+    b200msm_internal_compute_h_abort(ctxs[0]);
     for (int g = 0; g < n; ++g) {
         for (int l = 0; l < NLANES; ++l)
             if (ctxs[g]->lanes[l].pending) b200msm_wait(ctxs[g], l);
@@ -378,13 +382,14 @@ void prove_drain(b200msm_ctx *const *ctxs, int n) {
 
 // Second half: the H polynomial on shard 0's GPU beside the MSMs, its coefficients handed to the other shards over
 // NVLink, the H query, the fold of the partial points, the assembly and the proof bytes.
+// ca == nullptr: the three vectors have been staged already (b200msm_internal_compute_h_stage), only the finish is left.
 int prove_finish(b200msm_ctx *const *ctxs, b200msm_key *const *keys, int n, const uint64_t *ca, const uint64_t *cb, const uint64_t *cc,
                  Partials *P, uint8_t *proof) {
     b200msm_ctx *c0 = ctxs[0];
     const size_t d = keys[0]->d;
     const int dg = g2_deg(c0);
     const uint64_t *h_dev = nullptr;
-    int rc = b200msm_compute_h(c0, d, ca, cb, cc, nullptr, &h_dev);
+    int rc = ca ? b200msm_compute_h(c0, d, ca, cb, cc, nullptr, &h_dev) : b200msm_internal_compute_h_finish(c0, d, &h_dev);
     for (int g = 0; g < n && !rc; ++g) {
         const uint64_t *hs = h_dev + keys[g]->lo[4] * 12;
         if (g > 0) {
@@ -520,10 +525,16 @@ int b200msm_prove_sharded_file(b200msm_ctx *const *ctxs, b200msm_key *const *key
     std::vector<Partials> P((size_t)n);
     const double read_ns = double(h_bytes) / READ_BYTES_PER_NS;           // the FFTs cannot start before their input is here
     for (int g = 0; g < n && !rc; ++g) rc = prove_begin(ctxs[g], keys[g], w, r, read_ns, P[g]);
-    if (!rc && !read_range(fd, img + w_bytes, w_bytes, h_bytes)) rc = fail(ctx, B200MSM_ERR_ARG, "short read of %s", input_path);
+    // each coefficient vector is uploaded and transformed on shard 0's FFT stream while the next one is being read
+    const uint64_t *vec[3] = {ca, cb, cc};
+    for (int v = 0; v < 3 && !rc; ++v) {
+        const size_t off = w_bytes + (size_t)v * (h_bytes / 3);
+        if (!read_range(fd, img + off, off, h_bytes / 3)) rc = fail(ctx, B200MSM_ERR_ARG, "short read of %s", input_path);
+        else rc = b200msm_internal_compute_h_stage(ctx, d, v, vec[v]);
+    }
     close(fd);
     if (rc) { prove_drain(ctxs, n); return rc; }
-    return prove_finish(ctxs, keys, n, ca, cb, cc, P.data(), proof);
+    return prove_finish(ctxs, keys, n, nullptr, nullptr, nullptr, P.data(), proof);
 }
 
 int b200msm_prove(b200msm_ctx *ctx, const b200msm_key *key, const void *input_image, size_t bytes, uint8_t *proof) {
