@@ -6,12 +6,6 @@
 
 namespace {
 
-// a device allocation that is released on every return path
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { if (p) cudaFree(p); }
-};
-
 #ifndef B200_TREE_AFFINE_MIN
 #define B200_TREE_AFFINE_MIN 100000
 #endif
@@ -517,10 +511,10 @@ int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
     CU(cudaMalloc(&pre.p, n * EB));
     CU(cudaFuncSetAttribute(k_dbl_many<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DblCfg<G>::TS::SMEM));
     CU(cudaFuncSetAttribute(k_batch_normalise<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::TS::SMEM));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, 0));
+    EventPair ev;
+    CU(cudaEventCreate(&ev.e0));
+    CU(cudaEventCreate(&ev.e1));
+    CU(cudaEventRecord(ev.e0, 0));
     const unsigned lanes = TC::TPB * 32;
     const size_t runs = (n + B - 1) / B;
     const size_t tabw = n * 2 * (EB / 4);
@@ -539,12 +533,10 @@ int build_tables(b200msm_ctx *ctx, BaseSet &bs) {
         for (int t = by_doubling; t < bs.NT; ++t)
             k_psi_many<G><<<(unsigned)((n + lanes - 1) / lanes), TC::TS::THREADS, TC::TS::SMEM>>>((uint32_t)n, bs.pts + (size_t)(t - by_doubling) * tabw, bs.pts + (size_t)t * tabw);
     }
-    CU(cudaEventRecord(e1, 0));
+    CU(cudaEventRecord(ev.e1, 0));
     CU(cudaGetLastError());
-    CU(cudaEventSynchronize(e1));
-    CU(cudaEventElapsedTime(&bs.build_ms, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    CU(cudaEventSynchronize(ev.e1));
+    CU(cudaEventElapsedTime(&bs.build_ms, ev.e0, ev.e1));
     return B200MSM_OK;
 }
 
@@ -625,21 +617,19 @@ template <class G>
 int run_teammul_bench(b200msm_ctx *ctx, int blocks_per_sm, int iters, double *gops) {
     typedef BaCfg<G> C;
     CU(cudaFuncSetAttribute(k_mb_teammul<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::TS::SMEM));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    EventPair ev;
+    CU(cudaEventCreate(&ev.e0));
+    CU(cudaEventCreate(&ev.e1));
     const int blocks = ctx->sm_count * blocks_per_sm;
     for (int rep = 0; rep < 2; ++rep) {
-        CU(cudaEventRecord(e0, 0));
+        CU(cudaEventRecord(ev.e0, 0));
         k_mb_teammul<G><<<blocks, C::TS::THREADS, C::TS::SMEM>>>(iters, nullptr);
-        CU(cudaEventRecord(e1, 0));
-        CU(cudaEventSynchronize(e1));
+        CU(cudaEventRecord(ev.e1, 0));
+        CU(cudaEventSynchronize(ev.e1));
     }
     float ms = 0;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
+    CU(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
     CU(cudaGetLastError());
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
     *gops = double(blocks) * C::TPB * 32 * 2.0 * iters / (double(ms) * 1e6);
     return B200MSM_OK;
 }

@@ -120,6 +120,16 @@ int fail(b200msm_ctx *ctx, int code, const char *fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// a device allocation / a pair of timing events that are released on every return path (CU() returns early)
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+struct EventPair {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ~EventPair() { if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+};
+
 inline int degree_of(int curve, int group) { return group == B200MSM_G1 ? 1 : (curve == B200MSM_MNT4753 ? 2 : 3); }
 
 // ---- window-size / table choice ---------------------------------------------------------------

@@ -436,23 +436,21 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     CU(cudaSetDevice(ctx->device));
     if (kind >= 15) {  // register multiplier at 4 (kind 15), 8 (16) or 12 (17) warps per SM: does ONE warp per scheduler fill the pipe?
         if (kind > 17) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
-        uint32_t *dd = nullptr;
-        CU(cudaMalloc(&dd, 256));
-        cudaEvent_t a0, a1;
-        CU(cudaEventCreate(&a0));
-        CU(cudaEventCreate(&a1));
+        DevBuf buf;
+        CU(cudaMalloc(&buf.p, 256));
+        uint32_t *dd = static_cast<uint32_t *>(buf.p);
+        EventPair ev;
+        CU(cudaEventCreate(&ev.e0));
+        CU(cudaEventCreate(&ev.e1));
         const int nb = ctx->sm_count * (kind - 14);
         for (int rep = 0; rep < 2; ++rep) {
-            CU(cudaEventRecord(a0, 0));
+            CU(cudaEventRecord(ev.e0, 0));
             k_mb_fqmul<ModA><<<nb, 128>>>(dd, iters);
-            CU(cudaEventRecord(a1, 0));
-            CU(cudaEventSynchronize(a1));
+            CU(cudaEventRecord(ev.e1, 0));
+            CU(cudaEventSynchronize(ev.e1));
         }
         float ms = 0;
-        CU(cudaEventElapsedTime(&ms, a0, a1));
-        cudaEventDestroy(a0);
-        cudaEventDestroy(a1);
-        cudaFree(dd);
+        CU(cudaEventElapsedTime(&ms, ev.e0, ev.e1));
         *gops = double(nb) * 128 * iters / (double(ms) * 1e6);
         return B200MSM_OK;
     }
@@ -461,11 +459,13 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
         if (kind > 14) return fail(ctx, B200MSM_ERR_ARG, "bad argument");
         return ops_for(ctx->curve, group).teammul_bench(ctx, bps, iters, gops);
     }
-    uint32_t *d = nullptr;
-    CU(cudaMalloc(&d, 256));
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0));
-    CU(cudaEventCreate(&e1));
+    DevBuf buf;
+    CU(cudaMalloc(&buf.p, 256));
+    uint32_t *d = static_cast<uint32_t *>(buf.p);
+    EventPair ev;
+    CU(cudaEventCreate(&ev.e0));
+    CU(cudaEventCreate(&ev.e1));
+    cudaEvent_t e0 = ev.e0, e1 = ev.e1;
     const int blocks = ctx->sm_count * 8;
     double ops = 0;
     if (kind >= 4) {  // single-thread inversion latency: returns microseconds per inversion
@@ -481,9 +481,6 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
         CU(cudaEventElapsedTime(&ms, e0, e1));
         uint32_t h[2] = {0, 0};
         CU(cudaMemcpy(h, d, 8, cudaMemcpyDeviceToHost));
-        cudaEventDestroy(e0);
-        cudaEventDestroy(e1);
-        cudaFree(d);
         if (kind == 6 && h[1]) return fail(ctx, B200MSM_ERR_CUDA, "fast inversion failed its final check %u times", h[1]);
         *gops = double(ms) * 1e3 / iters;
         return B200MSM_OK;
@@ -503,9 +500,6 @@ int b200msm_microbench(b200msm_ctx *ctx, int kind, int iters, double *gops) {
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     CU(cudaGetLastError());
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
-    cudaFree(d);
     *gops = ops / (double(ms) * 1e6);
     return B200MSM_OK;
 }
