@@ -73,6 +73,23 @@ def emu():
 
 
 @pytest.fixture(scope="session")
+def warp_emu():
+    """The warp-cooperative device code (csrc/fq_inv_coop.cuh) on a simulated warp: 32 lanes in lock step with
+    shuffles and ballots (tests/host_emu/warp_sim.hpp)."""
+    import ctypes
+    d = os.path.join(ROOT, "tests", "host_emu")
+    so = os.path.join(d, "libwarpemu.so")
+    srcs = [os.path.join(d, "warp_emu.cpp"), os.path.join(d, "warp_sim.hpp")] + [
+        os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f) for f in ("prim.cuh", "fq.cuh", "fq_inv_coop.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU", "-x", "c++", srcs[0], "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    lib.emu_fq_inv_coop.argtypes = [ctypes.c_int, ctypes.c_size_t, u64p, u64p]
+    return lib
+
+
+@pytest.fixture(scope="session")
 def engine_lib():
     import gpu_groth16_prover_3x_b200 as pkg
     return pkg.load_library()

@@ -165,6 +165,22 @@ def test_emu_fq_inverse(emu, oracle, golden, modulus):
         assert failed == (nz if which else 0), which      # the fast path itself never needs the fallback (except for 0)
 
 
+@pytest.mark.parametrize("modulus", [0, 1])
+def test_warp_cooperative_inverse(warp_emu, oracle, modulus):
+    """csrc/fq_inv_coop.cuh -- ONE inversion by the 32 lanes of a warp, limb i on lane i, the tile inversion of the
+    batched-affine accumulation -- executed on a simulated warp (tests/host_emu/warp_sim.hpp: lock-step lanes, shuffles,
+    ballots, and a check that the lanes never diverge) against the oracle's field inversion.  Input and output are in
+    Montgomery form; 0 -> 0; the fast path never reports failure."""
+    rng = np.random.default_rng(23 + modulus)
+    p = po.fq_modulus(modulus)
+    edge = [0, 1, 2, 3, p - 1, p - 2, (p + 1) // 2, 1 << 752, (1 << 700) % p, po.R % p, po.R * po.R % p, 1 << 31, 1 << 32, (1 << 64) - 1]
+    edge += [pow(2, k, p) for k in (29, 30, 31, 59, 60, 61, 750)] + [(p - pow(2, k, p)) % p for k in (1, 30, 60)]
+    a = po.ints_to_array(edge + [int.from_bytes(rng.bytes(100), "little") % p for _ in range(40)])
+    out = np.zeros_like(a)
+    assert warp_emu.emu_fq_inv_coop(modulus, a.size // 12, _p(a), _p(out)) == 0
+    assert (out == oracle.field_op(modulus, 0, 4, a)).all()
+
+
 @pytest.mark.parametrize("curve,group", CG)
 def test_emu_tower_inverse(emu, oracle, golden, curve, group):
     """Team::inv_lane0: Fq by binary gcd, Fq2 / Fq3 through the norm (conjugate / Frobenius images)."""
