@@ -95,3 +95,27 @@ def test_compute_h_restatement_matches_reference_fixtures(oracle, golden, curve)
     for m in (2, 8, 64, 512):
         k = "c%d_m%d_" % (curve, m)
         assert (oracle.compute_h(curve, z[k + "ca"], z[k + "cb"], z[k + "cc"]) == z[k + "out"]).all(), m
+
+
+def test_constant_headers_are_the_generators():
+    """The committed constant headers -- the product's csrc/mnt753_constants.h (moduli, Montgomery constants, roots of
+    unity, generators, twist-Frobenius and scalar-split constants of csrc/glv.cuh) and the oracle's -- are byte for
+    byte what tools/gen_constants.py derives from the two primes.  Re-running the derivation re-runs its checks: the
+    2-adicity and roots of unity, the reduced lattice basis of the G2 scalar split and, on 2000 random and 9 edge
+    scalars, k0 + k1 (q mod r) = k (mod r) with |k0|, |k1| < 2^377."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_constants", os.path.join(root, "tools", "gen_constants.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    want = gen.emit(32, "MNT753_CONSTANTS_H", "/* 24 x 32-bit little-endian limbs, R = 2^768. */")
+    assert open(os.path.join(root, "gpu_groth16_prover_3x_b200", "csrc", "mnt753_constants.h")).read() == want
+    want = gen.emit(64, "ORACLE_CONSTANTS_H", "/* TEST INFRASTRUCTURE ONLY. 12 x 64-bit little-endian limbs, R = 2^768. */")
+    assert open(os.path.join(root, "oracle", "oracle_constants.h")).read() == want
+    for curve in (0, 1):
+        g = gen.glv_params(curve)
+        r = gen.MOD_B if curve == 0 else gen.MOD_A
+        for k in (0, 1, r - 1, g["lam"], (1 << 752) % r):
+            k0, k1 = g["split"](k)
+            assert (k0 + k1 * g["lam"] - k) % r == 0 and max(abs(k0), abs(k1)).bit_length() <= 377
