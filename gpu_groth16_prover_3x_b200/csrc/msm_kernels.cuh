@@ -18,6 +18,7 @@
 #include <cuda_runtime.h>
 
 #include "curves.cuh"
+#include "ba_plan.cuh"
 
 namespace mnt753 {
 
@@ -284,16 +285,6 @@ static __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t *out, uint3
     uint32_t add = bsum[blockIdx.x];
     for (int e = 0; e < SCAN_E; ++e)
         if (base + e < K) { uint32_t v = out[base + e] + add; out[base + e] = v; cursor[base + e] = v; }
-}
-
-// first index i in [0, n] with offs[i] > x, minus one  (offs non-decreasing, offs[0] = 0 <= x < offs[n])
-__device__ __forceinline__ uint32_t bucket_of(const uint32_t *offs, uint32_t n, uint32_t x) {
-    uint32_t lo = 0, hi = n;  // invariant: offs[lo] <= x < offs[hi]
-    while (hi - lo > 1) {
-        uint32_t mid = lo + ((hi - lo) >> 1);
-        if (offs[mid] <= x) lo = mid; else hi = mid;
-    }
-    return lo;
 }
 
 // ------------------------------------------------------------------------------------------

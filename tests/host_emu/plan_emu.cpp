@@ -1,0 +1,259 @@
+// CPU model check of the round planning of the batched-affine bucket accumulation: the REAL csrc/ba_plan.cuh
+// (ba_boundary, ba_plan with its warp shuffles, the scratch-slot formulas) runs on a simulated warp (warp_sim.hpp);
+// the additions themselves are replaced by set unions of entry ids.  What the model checks:
+//   * every source a pass reads holds the point it is supposed to hold (a scratch slot is never rewritten -- by a
+//     prefix product of the forward pass or by a later sum -- while a reference to it is still going to be read);
+//   * every sum and prefix lands inside the region the host sized for it (capA / capB / the fix-up's regions: the
+//     formulas of make_plan, csrc/group_ops.cuh), and inside the part of it that belongs to the share;
+//   * after all rounds every bucket is exactly the union of its entries -- whole buckets through bucket_ref, buckets
+//     cut between shares through the boundary list and the fix-up's rounds.
+// The share loop, the tile walk and the fix-up's compaction are restated here from k_batch_add / ba_share / ba_tile /
+// k_ba_fixup (batch_affine.cuh); the planning they call is the shipped code.  Test-only.
+#include "warp_sim.hpp"
+
+#include <algorithm>
+#include <map>
+#include <string>
+
+struct uint4 { uint32_t x, y, z, w; };
+static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+#include "../../gpu_groth16_prover_3x_b200/csrc/ba_plan.cuh"
+
+using namespace mnt753;
+
+namespace {
+
+typedef std::vector<uint32_t> Ids;      // sorted entry ids = the "point"
+
+struct Model {
+    std::string err;
+    std::map<uint32_t, Ids> slot;        // scratch slot -> point; an empty vector marks a parked prefix product
+    std::map<uint32_t, int> owner;       // scratch slot -> share that wrote it (-1: the fix-up)
+    uint64_t capA = 0, capB = 0, capF = 0;
+    uint32_t cancel_every = 0, additions = 0;   // every cancel_every-th addition sums to infinity (P + (-P)) ...
+    Ids lost;                                   // ... and its entries leave their bucket
+    bool fail(const std::string &m) { if (err.empty()) err = m; return false; }
+
+    bool read(uint32_t ref, Ids &out) {
+        if (ref == REF_INF) return fail("an infinite operand reached a pass");
+        if (!(ref & REF_SCRATCH)) { out.assign(1, ref & REF_IDX); return true; }      // a table row: entry id = row
+        auto it = slot.find(ref & REF_IDX);
+        if (it == slot.end()) return fail("read of scratch slot " + std::to_string(ref & REF_IDX) + " that was never written");
+        if (it->second.empty()) return fail("read of scratch slot " + std::to_string(ref & REF_IDX) + " while it holds a prefix product");
+        out = it->second;
+        return true;
+    }
+    bool write(uint32_t s, const Ids &v, int share, uint64_t lo, uint64_t hi) {
+        if (s < lo || s >= hi) return fail("scratch slot " + std::to_string(s) + " outside [" + std::to_string(lo) + ", " + std::to_string(hi) + ") of its region");
+        auto it = owner.find(s);
+        if (it != owner.end() && it->second != share) return fail("scratch slot " + std::to_string(s) + " written by two shares");
+        owner[s] = share;
+        slot[s] = v;
+        return true;
+    }
+};
+
+// one share through all its rounds (ba_share + ba_tile of batch_affine.cuh, with unions for additions)
+bool run_share(Model &M, const BaArgs &a, const BaView &v, int share, uint32_t bmax, uint32_t &rounds_out) {
+    const uint64_t regA_lo = share < 0 ? a.fx_scratch_base : 0, regA_hi = share < 0 ? a.fx_scratch_base + a.U + 1 : M.capA;
+    const uint64_t regB_lo = share < 0 ? a.fx_scratch_base + a.U + 1 : M.capA, regB_hi = share < 0 ? a.fx_scratch_base + M.capF : M.capA + M.capB;
+    uint32_t r = 0;
+    for (;; ++r) {
+        uint32_t P[warpsim::LANES];
+        warpsim::run_warp([&](int lane) {
+            uint32_t maxc = 0;
+            P[lane] = ba_plan(v, r, lane, maxc);
+        });
+        for (int l = 1; l < warpsim::LANES; ++l)
+            if (P[l] != P[0]) return M.fail("ba_plan returned different pair counts on different lanes");
+        if (P[0] == 0) break;
+        if (r > 40) return M.fail("rounds do not terminate");
+        uint32_t *nxt = v.refs[(r + 1u) & 1u];
+        const uint64_t lo = (r & 1u) ? regB_lo : regA_lo, hi = (r & 1u) ? regB_hi : regA_hi;
+        uint32_t p0 = 0;
+        while (p0 < P[0]) {
+            const uint32_t left = (P[0] - p0 + 31u) / 32u;
+            uint32_t B = left;
+            if (left > bmax) B = left >= 2u * bmax ? bmax : (left + 1u) / 2u;
+            const uint4 idle = make_uint4(REF_INF, REF_INF, 0u, 0u);
+            // forward: abscissae of both operands are read, the prefix is parked in the output slot
+            for (uint32_t i = 0; i < B; ++i)
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const uint32_t p = p0 + i * 32u + lane;
+                    const uint4 d = p < P[0] ? v.pairs[p] : idle;
+                    if (d.x == REF_INF) continue;
+                    Ids t;
+                    if (!M.read(d.x, t)) return false;
+                    if (d.y != REF_INF && !M.read(d.y, t)) return false;
+                    if (!M.write(d.z, Ids(), share, lo, hi)) return false;
+                }
+            // backward: both operands and the prefix are read, the sum replaces the prefix
+            for (int i = (int)B - 1; i >= 0; --i)
+                for (uint32_t lane = 0; lane < 32; ++lane) {
+                    const uint32_t p = p0 + (uint32_t)i * 32u + lane;
+                    const uint4 d = p < P[0] ? v.pairs[p] : idle;
+                    if (d.x == REF_INF) continue;
+                    Ids s1, s2;
+                    if (!M.read(d.x, s1)) return false;
+                    if (d.y != REF_INF && !M.read(d.y, s2)) return false;
+                    auto it = M.slot.find(d.z);
+                    if (it == M.slot.end() || !it->second.empty()) return M.fail("the prefix parked in slot " + std::to_string(d.z) + " was overwritten before the backward pass");
+                    Ids sum(s1.size() + s2.size());
+                    std::merge(s1.begin(), s1.end(), s2.begin(), s2.end(), sum.begin());
+                    const bool cancel = d.y != REF_INF && M.cancel_every && ++M.additions % M.cancel_every == 0;
+                    if (cancel) {           // the kernel writes zeros to the slot and hands infinity on
+                        M.lost.insert(M.lost.end(), sum.begin(), sum.end());
+                        sum.assign(1, 0xfffffffeu);
+                    }
+                    if (!M.write(d.z, sum, share, lo, hi)) return false;
+                    nxt[d.w] = cancel ? REF_INF : (REF_SCRATCH | d.z);
+                }
+            p0 += 32u * B;
+        }
+    }
+    rounds_out = r;
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+// counts[K]: points per bucket (the sorted list is 0, 1, 2, ... grouped by bucket), U shares, bmax additions per lane
+// and tile, every cancel_every-th addition (0: none) sums to infinity.  Returns 0 when the model holds, 1 otherwise (message in err, at most errlen bytes).  stats[0] = most
+// rounds of a share, [1] = buckets cut between shares, [2] = scratch slots written.
+int emu_plan_check(uint32_t K, const uint32_t *counts, uint32_t U, uint32_t bmax, uint32_t cancel_every, uint64_t *stats, char *err, size_t errlen) {
+    std::vector<uint32_t> offs(K + 1, 0);
+    for (uint32_t b = 0; b < K; ++b) offs[b + 1] = offs[b] + counts[b];
+    const uint32_t E = offs[K];
+    if (E >= (1u << 30)) return 2;
+    Model M;
+    M.cancel_every = cancel_every;
+    // capacities as the host sizes them (make_plan, csrc/group_ops.cuh): emax = E here
+    M.capA = (uint64_t)E / 2 + 1;
+    M.capB = ((uint64_t)E + K + U) / 4 + 2;
+    M.capF = 2 * (uint64_t)U + 2;
+    std::vector<uint32_t> refs0(E + 1), refs1(E + 1, 0), cntv(K + U, 0), bucket_ref(K, REF_INF), bnd_ref(2 * U, REF_INF), bnd_bucket(2 * U, REF_INF);
+    std::vector<uint4> pairs((size_t)E / 2 + U + 1);
+    for (uint32_t e = 0; e < E; ++e) refs0[e] = e;
+    BaArgs a;
+    memset(&a, 0, sizeof a);
+    a.K = K;
+    a.U = U;
+    a.offs = offs.data();
+    a.refs[0] = refs0.data();
+    a.refs[1] = refs1.data();
+    a.capA = (uint32_t)M.capA;
+    a.pairs = pairs.data();
+    a.cntv = cntv.data();
+    a.bucket_ref = bucket_ref.data();
+    a.bnd_ref = bnd_ref.data();
+    a.bnd_bucket = bnd_bucket.data();
+    a.fx_scratch_base = (uint32_t)(M.capA + M.capB);
+    a.T = std::max<uint32_t>(1u, (E + U - 1u) / U);
+    uint32_t max_rounds = 0, cut = 0;
+    bool ok = true;
+    // ---- k_batch_add: every share through its rounds, then what is left of its pieces
+    for (uint32_t t = 0; t < U && ok; ++t) {
+        const uint32_t E0 = ba_boundary(a, t, E), E1 = ba_boundary(a, t + 1u, E);
+        if (E0 > E1) { ok = M.fail("share boundaries are not monotone"); break; }
+        if (E0 >= E1) continue;
+        BaView v;
+        v.offs = a.offs;
+        v.E0 = E0;
+        v.E1 = E1;
+        v.b0 = bucket_of(a.offs, a.K, E0);
+        const uint32_t b1 = bucket_of(a.offs, a.K, E1 - 1u);
+        v.npieces = b1 - v.b0 + 1u;
+        v.id = t;
+        v.refs[0] = a.refs[0];
+        v.refs[1] = a.refs[1];
+        v.cntv = a.cntv;
+        v.pairs = a.pairs + (E0 >> 1) + t;
+        v.codes = nullptr;
+        v.a_base = 0u;
+        v.b_base = a.capA;
+        uint32_t rounds = 0;
+        ok = run_share(M, a, v, (int)t, bmax, rounds);
+        if (!ok) break;
+        max_rounds = std::max(max_rounds, rounds);
+        const uint32_t *cur = a.refs[rounds & 1u];
+        for (uint32_t q = 0; q < v.npieces; ++q) {
+            const uint32_t b = v.b0 + q;
+            const uint32_t lo = a.offs[b], hi = a.offs[b + 1];
+            const uint32_t ps = std::max(lo, v.E0), pe = std::min(hi, v.E1);
+            const uint32_t c = rounds ? a.cntv[b + t] : pe - ps;
+            const uint32_t ref = c ? cur[ps] : REF_INF;
+            if (c > 1u) { ok = M.fail("a piece is left with more than one point"); break; }
+            if (lo >= v.E0 && hi <= v.E1) a.bucket_ref[b] = ref;
+            else {
+                const uint32_t s = 2u * t + (lo < v.E0 ? 0u : 1u);
+                if (a.bnd_bucket[s] != REF_INF) { ok = M.fail("two cut pieces in one boundary slot"); break; }
+                a.bnd_ref[s] = ref;
+                a.bnd_bucket[s] = b;
+            }
+        }
+    }
+    // the shares must tile the list: every entry belongs to exactly one of them (monotone boundaries from 0 to E)
+    if (ok && (ba_boundary(a, 0, E) != 0u || ba_boundary(a, U, E) != E)) ok = M.fail("the shares do not cover the list");
+    // ---- k_ba_fixup: the cut pieces as a list of their own (slot order = list order), reduced by the same rounds
+    if (ok) {
+        std::vector<uint32_t> fr0(2 * U + 1, REF_INF), fr1(2 * U + 1, REF_INF), foffs, fbucket, fcntv(2 * U + 1, 0);
+        uint32_t n = 0, prev = REF_INF;
+        for (uint32_t i = 0; i < 2 * U; ++i) {
+            if (a.bnd_bucket[i] == REF_INF) continue;
+            if (a.bnd_bucket[i] != prev) { foffs.push_back(n); fbucket.push_back(a.bnd_bucket[i]); prev = a.bnd_bucket[i]; }
+            fr0[n++] = a.bnd_ref[i];
+        }
+        foffs.push_back(n);
+        cut = (uint32_t)fbucket.size();
+        if (n) {
+            std::vector<uint4> fpairs((size_t)n / 2 + 2);
+            BaView v;
+            v.offs = foffs.data();
+            v.E0 = 0u;
+            v.E1 = n;
+            v.b0 = 0u;
+            v.npieces = cut;
+            v.id = 0u;
+            v.refs[0] = fr0.data();
+            v.refs[1] = fr1.data();
+            v.cntv = fcntv.data();
+            v.pairs = fpairs.data();
+            v.codes = nullptr;
+            v.a_base = a.fx_scratch_base;
+            v.b_base = a.fx_scratch_base + a.U + 1u;
+            uint32_t rounds = 0;
+            ok = run_share(M, a, v, -1, bmax, rounds);
+            if (ok) {
+                const uint32_t *cur = rounds & 1u ? fr1.data() : fr0.data();
+                for (uint32_t q = 0; q < cut; ++q) {
+                    const uint32_t ps = foffs[q];
+                    const uint32_t c = rounds ? fcntv[q] : foffs[q + 1] - ps;
+                    if (a.bucket_ref[fbucket[q]] != REF_INF) { ok = M.fail("a cut bucket already has a final reference"); break; }
+                    a.bucket_ref[fbucket[q]] = c ? cur[ps] : REF_INF;
+                }
+            }
+        }
+    }
+    // ---- every bucket is the union of its entries (minus what cancelled)
+    std::sort(M.lost.begin(), M.lost.end());
+    for (uint32_t b = 0; b < K && ok; ++b) {
+        const uint32_t ref = a.bucket_ref[b];
+        Ids want;
+        for (uint32_t i = 0; i < counts[b]; ++i)
+            if (!std::binary_search(M.lost.begin(), M.lost.end(), offs[b] + i)) want.push_back(offs[b] + i);
+        if (want.empty()) { if (ref != REF_INF) ok = M.fail("bucket " + std::to_string(b) + " should be empty"); continue; }
+        Ids got;
+        if (ref == REF_INF) { ok = M.fail("bucket " + std::to_string(b) + " lost its points"); break; }
+        if (!M.read(ref, got)) { ok = false; break; }
+        if (got != want) ok = M.fail("bucket " + std::to_string(b) + " is not the sum of its entries");
+    }
+    if (stats) { stats[0] = max_rounds; stats[1] = cut; stats[2] = M.slot.size(); }
+    if (err && errlen) { strncpy(err, M.err.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return ok ? 0 : 1;
+}
+}

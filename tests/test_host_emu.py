@@ -232,3 +232,31 @@ def test_emu_batched_affine_pair(emu, oracle, golden, curve, group):
         assert inf == 0 and (out == p).all()
     out, inf = run(pts[3], pts[4])
     assert (out == oracle.point_op(curve, group, 0, pts[3], pts[4])).all()
+
+
+def test_round_planning_model_check(plan_emu):
+    """csrc/ba_plan.cuh -- the cut of the sorted list into shares, the plan of every round of every share (pairs dealt
+    over the lanes with shuffles, odd one carried over, infinite operands) and the formulas that recycle scratch slots
+    every second round -- executed on a simulated warp, with a set of entry ids for every point and unions for additions
+    (tests/host_emu/plan_emu.cpp).  Checked: no slot is rewritten while a reference to it is still to be read, no two
+    shares write the same slot, every slot lies inside the region the host sized for it, the pieces of buckets cut between
+    shares meet again in the fix-up, and every bucket ends as exactly the union of its entries -- also when sums cancel
+    to infinity, with tiles of a single addition per lane, with more shares than entries and with giant buckets."""
+    import ctypes
+    rng = np.random.default_rng(7)
+    cases = [(np.array([3, 0, 400, 350, 1, 0, 2]), 12), (np.array([0, 0, 777, 0]), 10), (np.array([1, 2, 0, 1]), 8),
+             (np.ones(100, np.uint32), 7), (np.zeros(10, np.uint32), 4), (rng.poisson(2.5, 600), 16), (rng.poisson(20, 64), 1)]
+    for _ in range(28):
+        counts = rng.poisson(rng.choice([0.3, 2, 9]), int(rng.integers(1, 40)))
+        for _ in range(int(rng.integers(0, 3))):
+            counts[rng.integers(0, len(counts))] = rng.integers(50, 900)
+        cases.append((counts, int(rng.integers(1, 40))))
+    cut = 0
+    for i, (counts, shares) in enumerate(cases):
+        c = np.ascontiguousarray(counts, dtype=np.uint32)
+        stats, err = (ctypes.c_uint64 * 3)(), ctypes.create_string_buffer(300)
+        rc = plan_emu.emu_plan_check(len(c), c.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), shares, (2048, 1, 5)[i % 3], (0, 3, 0, 7)[i % 4],
+                                     stats, err, 300)
+        assert rc == 0, (list(c), shares, err.value.decode())
+        cut += stats[1]
+    assert cut > 20          # buckets cut between shares were part of it
