@@ -400,7 +400,10 @@ def run_b200(args):
     roofline = {
         "kernel": "k_batch_add (all rounds of one MSM)", "bound": "imad",
         "field_muls_per_addition": muls_per_add, "achieved": achieved, "peak": peak, "unit": "GMAC/s", "frac": achieved / peak,
-        "traffic": traffic, "launch_ms": acc_ms, "share_of_step": acc_ms / (dev_s / args.steps * 1e3),
+        # DRAM bytes of one launch of the dominant kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+        # capture, committed under profiles/); the capture it comes from is described in traffic_detail
+        "traffic": traffic["bytes"] if traffic else None, "traffic_detail": traffic,
+        "launch_ms": acc_ms, "share_of_step": acc_ms / (dev_s / args.steps * 1e3),
         "peak_source": "measured in this run: max(IMAD.WIDE.U32 stream, Fq Montgomery product in registers x 1176 MAC); "
                        "a 32x32->64 multiply-add issues at 32 per clock per SM on B200 (tools/pipe_probe.cu)",
         "macs_per_launch": macs_per_launch, "micro": micro,
