@@ -23,6 +23,14 @@ def test_header_symbols_exported(engine_lib):
         assert hasattr(engine_lib, s), "libb200msm.so does not export %s" % s
 
 
+def test_every_symbol_is_documented():
+    """INTEGRATION.md names every entry point of the header (in full, or as `_suffix` / `create/destroy` shorthand)."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    for s in declared_symbols():
+        short = s[len("b200msm"):]
+        assert s in doc or short in doc or short.lstrip("_") in doc, "INTEGRATION.md does not mention %s" % s
+
+
 def test_no_oracle_in_product():
     """The product path never touches oracle/ (no import, no dlopen, no link)."""
     pk = os.path.join(ROOT, "gpu_groth16_prover_3x_b200")
