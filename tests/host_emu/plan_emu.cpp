@@ -8,7 +8,8 @@
 //   * after all rounds every bucket is exactly the union of its entries -- whole buckets through bucket_ref, buckets
 //     cut between shares through the boundary list and the fix-up's rounds.
 // The share loop, the tile walk and the fix-up's compaction are restated here from k_batch_add / ba_share / ba_tile /
-// k_ba_fixup (batch_affine.cuh); the planning they call is the shipped code.  Test-only.
+// k_ba_fixup (batch_affine.cuh); the planning they call is the shipped code.  A second model, at the end of the file,
+// does the same for the index logic of the bucket-reduction tree (csrc/tree_plan.cuh).  Test-only.
 #include "warp_sim.hpp"
 
 #include <algorithm>
@@ -21,6 +22,7 @@ static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 #include "../../gpu_groth16_prover_3x_b200/csrc/ba_plan.cuh"
+#include "../../gpu_groth16_prover_3x_b200/csrc/tree_plan.cuh"
 
 using namespace mnt753;
 
@@ -254,6 +256,133 @@ int emu_plan_check(uint32_t K, const uint32_t *counts, uint32_t U, uint32_t bmax
     }
     if (stats) { stats[0] = max_rounds; stats[1] = cut; stats[2] = M.slot.size(); }
     if (err && errlen) { strncpy(err, M.err.c_str(), errlen - 1); err[errlen - 1] = 0; }
+    return ok ? 0 : 1;
+}
+
+// ---- the bucket-reduction tree (csrc/tree_plan.cuh, bucket_tree.cuh) with integers modulo 2^61 - 1 for points ----------
+// val[W * 2^k]: the bucket sums left by the accumulation, 0 = empty bucket.  Rounds 1 .. h run TreePairs::passthrough /
+// get / locate (the shipped index code) as k_tree_round (r <= hA) or k_tree_jac (r > hA) do; the k + 1 short lists and
+// the window sum are restated from k_tree_finish / k_sum.  Checked: every input of a round was written by an EARLIER
+// round (or is a bucket), every node is written exactly once, Jacobian nodes fall inside the J array the host sized
+// (make_plan), and the result of every set is sum_b (b + 1) B_b.  Returns 0 / 1 (message in err).
+int emu_tree_check(uint32_t W, uint32_t k, uint32_t hA_in, const uint64_t *val, char *err, size_t errlen) {
+    const uint64_t MOD = (uint64_t(1) << 61) - 1;
+    auto addm = [&](uint64_t a, uint64_t b) { const uint64_t s = a + b; return s >= MOD ? s - MOD : s; };
+    std::string msg;
+    auto fail = [&](const std::string &m) { if (msg.empty()) msg = m; return false; };
+    TreeArgs t;
+    memset(&t, 0, sizeof t);
+    t.W = W;
+    t.k = k;
+    t.NB = 1u << k;
+    t.h = k > 5u ? k - 5u : 0u;
+    t.hA = std::min(hA_in, t.h);
+    t.nodes = 2u * t.NB;
+    t.jbase = t.hA < t.h ? t.NB - (t.NB >> t.hA) : t.nodes;
+    t.jnodes = t.nodes - t.jbase;
+    t.slot_base = 1000u;
+    std::vector<uint32_t> bucket_ref((size_t)W * t.NB), R((size_t)W * t.nodes, 0xdeadbeefu);
+    std::vector<int> written((size_t)W * t.nodes, -1);           // round that wrote the node
+    std::vector<uint64_t> nodeval((size_t)W * t.nodes, 0), jval((size_t)W * t.jnodes + 1, 0);
+    for (size_t i = 0; i < bucket_ref.size(); ++i) bucket_ref[i] = val[i] ? (uint32_t)i : REF_INF;     // a table row per bucket
+    t.bucket_ref = bucket_ref.data();
+    t.R = R.data();
+    bool ok = true;
+    int round = 0;
+    // value behind a reference; inputs must come from an earlier round
+    auto value = [&](uint32_t ref, uint32_t set, uint64_t &out) -> bool {
+        if (ref == REF_INF) { out = 0; return true; }
+        if ((ref & REF_JAC) == REF_JAC) {
+            const uint32_t node = ref & REF_IDX;
+            const long long j = (long long)node - (long long)set * t.nodes - (long long)t.jbase;
+            if (j < 0 || j >= (long long)t.jnodes) return fail("Jacobian node " + std::to_string(node) + " outside the J array");
+            if (written[node] < 0 || written[node] >= round) return fail("Jacobian node read before it was written");
+            out = jval[(size_t)set * t.jnodes + (size_t)j];
+            return true;
+        }
+        if (ref & REF_SCRATCH) {
+            const uint32_t slot = ref & REF_IDX;
+            if (slot < t.slot_base || slot - t.slot_base >= W * t.nodes) return fail("scratch reference outside the tree's slots");
+            const uint32_t node = slot - t.slot_base;
+            if (written[node] < 0 || written[node] >= round) return fail("node " + std::to_string(node) + " read in the round that writes it (or never written)");
+            out = nodeval[node];
+            return true;
+        }
+        if (ref >= bucket_ref.size()) return fail("table reference out of range");
+        out = val[ref];
+        return true;
+    };
+    auto own_set = [&](const uint32_t *ptr) -> bool {        // an input pointer must lie in bucket_ref or R
+        return (ptr >= bucket_ref.data() && ptr < bucket_ref.data() + bucket_ref.size()) || (ptr >= R.data() && ptr < R.data() + R.size());
+    };
+    for (uint32_t r = 1; r <= t.h && ok; ++r) {
+        round = (int)r;
+        t.r = r;
+        t.q = t.NB >> (r + 1);
+        t.logq = t.k - (r + 1);
+        t.P = t.W * t.q * (2u + r);
+        const TreePairs src{t, nullptr, t.P};
+        std::vector<std::pair<uint32_t, uint32_t>> wr;       // (node, reference) written this round, applied afterwards
+        std::vector<std::pair<uint32_t, uint64_t>> wv;
+        for (uint32_t p = 0; p < t.P && ok; ++p) {
+            const uint32_t *i0, *i1;
+            uint32_t node;
+            src.locate(p, i0, i1, node);
+            if (!own_set(i0) || !own_set(i1)) { ok = fail("an input of round " + std::to_string(r) + " lies outside the reference arrays"); break; }
+            if (node >= W * t.nodes) { ok = fail("node out of range"); break; }
+            if (written[node] >= 0) { ok = fail("node " + std::to_string(node) + " written twice"); break; }
+            const uint32_t set = node / t.nodes;
+            const uint32_t r0 = *i0, r1 = *i1;
+            uint64_t v0, v1;
+            if (!value(r0, set, v0) || !value(r1, set, v1)) { ok = false; break; }
+            if (r <= t.hA) {
+                // k_tree_round: passthrough for an empty operand, an affine addition otherwise
+                const uint4 d = src.get(p);
+                if (r0 == REF_INF || r1 == REF_INF) {
+                    if (d.x != REF_INF) { ok = fail("get() returned an addition for an empty operand"); break; }
+                    wr.push_back({node, r0 == REF_INF ? r1 : r0});
+                } else {
+                    if (d.x != r0 || d.y != r1 || d.w != node || d.z != t.slot_base + node) { ok = fail("get() and locate() disagree"); break; }
+                    wr.push_back({node, REF_SCRATCH | d.z});
+                    wv.push_back({node, addm(v0, v1)});
+                }
+            } else {
+                // k_tree_jac: always a Jacobian node (infinity when both operands are empty)
+                const long long j = (long long)node - (long long)set * t.nodes - (long long)t.jbase;
+                if (j < 0 || j >= (long long)t.jnodes) { ok = fail("round " + std::to_string(r) + ": Jacobian node " + std::to_string(node) + " outside the J array"); break; }
+                jval[(size_t)set * t.jnodes + (size_t)j] = addm(v0, v1);
+                wr.push_back({node, REF_JAC | node});
+            }
+            written[node] = (int)r;
+        }
+        for (auto &w : wr) R[w.first] = w.second;
+        for (auto &w : wv) nodeval[w.first] = w.second;
+    }
+    // ---- k_tree_finish + k_sum: the k + 1 short lists of every set
+    round = (int)t.h + 1;
+    for (uint32_t set = 0; set < W && ok; ++set) {
+        uint64_t total = 0;
+        const uint32_t nt = t.NB >> t.h;
+        for (uint32_t l = 0; l <= t.k && ok; ++l) {
+            uint64_t term = 0;
+            for (uint32_t lane = 0; lane < 32u && ok; ++lane) {
+                uint32_t ref = REF_INF;
+                if (l == 0u) { if (lane < nt) ref = tree_tlist(t, set, t.h)[lane]; }
+                else if (l - 1u < t.h) { if (lane < (nt >> 1)) ref = t.R[(size_t)set * t.nodes + tree_ooff(t, l - 1u, t.h - (l - 1u)) + lane]; }
+                else if (lane < nt && ((lane >> (l - 1u - t.h)) & 1u)) ref = tree_tlist(t, set, t.h)[lane];
+                uint64_t v;
+                if (!value(ref, set, v)) { ok = false; break; }
+                term = addm(term, v);
+            }
+            for (uint32_t i = 1; i < l; ++i) term = addm(term, term);          // l = 1 + j: j doublings
+            total = addm(total, term);
+        }
+        if (!ok) break;
+        uint64_t want = 0;
+        for (uint32_t b = 0; b < t.NB; ++b) want = (uint64_t)(((unsigned __int128)want + (unsigned __int128)(b + 1u) * val[(size_t)set * t.NB + b]) % MOD);
+        if (total != want) ok = fail("set " + std::to_string(set) + ": the tree does not sum to sum_b (b + 1) B_b");
+    }
+    if (err && errlen) { strncpy(err, msg.c_str(), errlen - 1); err[errlen - 1] = 0; }
     return ok ? 0 : 1;
 }
 }

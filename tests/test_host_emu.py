@@ -260,3 +260,25 @@ def test_round_planning_model_check(plan_emu):
         assert rc == 0, (list(c), shares, err.value.decode())
         cut += stats[1]
     assert cut > 20          # buckets cut between shares were part of it
+
+
+def test_reduction_tree_model_check(plan_emu):
+    """csrc/tree_plan.cuh -- the node layout of the bucket-reduction tree and, for every addition of every round, its two
+    inputs and its node (TreePairs::locate / get / passthrough, the shipped code) -- executed with integers modulo
+    2^61 - 1 for points (tests/host_emu/plan_emu.cpp).  Checked: every input of a round was written by an earlier round,
+    every node is written once, Jacobian nodes fall inside the array the host sized, and the k + 1 terms of every set add
+    up to sum_b (b + 1) B_b -- for 2 .. 2048 buckets per set, one to three sets, any split between affine and Jacobian
+    rounds, full, sparse and empty bucket sets."""
+    import ctypes
+    rng = np.random.default_rng(3)
+    mod = (1 << 61) - 1
+    for k in range(1, 12):
+        h = max(0, k - 5)
+        for sets in (1, 3):
+            for affine_rounds in sorted({0, h // 2, h}):
+                for fill in (1.0, 0.5, 0.05, 0.0):
+                    val = rng.integers(1, mod, sets << k, dtype=np.uint64)
+                    val[rng.random(sets << k) >= fill] = 0
+                    err = ctypes.create_string_buffer(300)
+                    rc = plan_emu.emu_tree_check(sets, k, affine_rounds, val.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), err, 300)
+                    assert rc == 0, (k, sets, affine_rounds, fill, err.value.decode())
