@@ -23,6 +23,7 @@ static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 #include "../../gpu_groth16_prover_3x_b200/csrc/ba_plan.cuh"
 #include "../../gpu_groth16_prover_3x_b200/csrc/tree_plan.cuh"
+#include "../../gpu_groth16_prover_3x_b200/csrc/recode.cuh"
 
 using namespace mnt753;
 
@@ -384,5 +385,11 @@ int emu_tree_check(uint32_t W, uint32_t k, uint32_t hA_in, const uint64_t *val, 
     }
     if (err && errlen) { strncpy(err, msg.c_str(), errlen - 1); err[errlen - 1] = 0; }
     return ok ? 0 : 1;
+}
+
+// ---- signed-digit recoding (csrc/recode.cuh): the W digits of the nl-limb integer k for window width c ----------------
+void emu_recode(const uint32_t *k, int nl, int c, int W, int32_t *digits) {
+    for (int w = 0; w < W; ++w) digits[w] = 0;
+    for_each_digit(k, nl, c, W, [&](int w, int d) { digits[w] = d; });
 }
 }

@@ -282,3 +282,25 @@ def test_reduction_tree_model_check(plan_emu):
                     err = ctypes.create_string_buffer(300)
                     rc = plan_emu.emu_tree_check(sets, k, affine_rounds, val.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), err, 300)
                     assert rc == 0, (k, sets, affine_rounds, fill, err.value.decode())
+
+
+def test_signed_digit_recoding(plan_emu):
+    """csrc/recode.cuh (the digits k_count / k_scatter sort by), for every window width 2 .. 22: the W = ceil(754 / c)
+    signed digits of a 753-bit scalar lie in [-2^(c-1) + 1, 2^(c-1)] and sum_w d_w 2^(c w) is the scalar again -- no
+    borrow is lost beyond the top window -- and the same for the 12-limb halves of a split G2 scalar (|k| < 2^377,
+    ceil(378 / c) digits, csrc/glv.cuh)."""
+    import ctypes
+    rng = np.random.default_rng(17)
+    r = po.fr_modulus(0)
+    full = [0, 1, 2, (1 << 753) - 1, r - 1, r - 2, 1 << 752, (1 << 752) - 1, int("5" * 226, 16) % (1 << 753), int("a" * 188, 16)]
+    full += [int.from_bytes(rng.bytes(96), "little") % (1 << 753) for _ in range(40)]
+    half = [0, 1, (1 << 377) - 1, 1 << 376, (1 << 376) - 1] + [int.from_bytes(rng.bytes(48), "little") % (1 << 377) for _ in range(40)]
+    for c in range(2, 23):
+        for vals, nl, bits in ((full, 24, 754), (half, 12, 378)):
+            w = (bits + c - 1) // c
+            for k in vals:
+                limbs = np.frombuffer(k.to_bytes(4 * nl, "little"), dtype=np.uint32).copy()
+                digits = np.zeros(w, np.int32)
+                plan_emu.emu_recode(limbs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), nl, c, w, digits.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
+                assert digits.min() >= -(1 << (c - 1)) + 1 and digits.max() <= 1 << (c - 1), (c, k)
+                assert sum(int(d) << (c * i) for i, d in enumerate(digits)) == k, (c, k)
