@@ -97,7 +97,7 @@ def plan_emu():
     d = os.path.join(ROOT, "tests", "host_emu")
     so = os.path.join(d, "libplanemu.so")
     srcs = [os.path.join(d, "plan_emu.cpp"), os.path.join(d, "warp_sim.hpp")] + [os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f)
-                                                                                 for f in ("ba_plan.cuh", "tree_plan.cuh", "recode.cuh")]
+                                                                                 for f in ("ba_plan.cuh", "tree_plan.cuh", "recode.cuh", "glv_split.cuh", "fq.cuh", "prim.cuh", "mnt753_constants.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU", "-x", "c++", srcs[0], "-o", so], check=True)
     lib = ctypes.CDLL(so)
@@ -105,6 +105,8 @@ def plan_emu():
                                    ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
     lib.emu_recode.argtypes = [ctypes.POINTER(ctypes.c_uint32), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int32)]
     lib.emu_recode.restype = None
+    lib.emu_glv_split.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint32)]
+    lib.emu_glv_split.restype = None
     lib.emu_tree_check.argtypes = [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint64), ctypes.c_char_p, ctypes.c_size_t]
     return lib
 

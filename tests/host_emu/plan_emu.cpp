@@ -16,7 +16,7 @@
 #include <map>
 #include <string>
 
-struct uint4 { uint32_t x, y, z, w; };
+#include "../../gpu_groth16_prover_3x_b200/csrc/prim.cuh"      // uint4 and the carry-chain primitives of the host emulation
 static inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
 static inline uint32_t max(uint32_t a, uint32_t b) { return a > b ? a : b; }
 static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -24,6 +24,7 @@ static inline uint32_t min(uint32_t a, uint32_t b) { return a < b ? a : b; }
 #include "../../gpu_groth16_prover_3x_b200/csrc/ba_plan.cuh"
 #include "../../gpu_groth16_prover_3x_b200/csrc/tree_plan.cuh"
 #include "../../gpu_groth16_prover_3x_b200/csrc/recode.cuh"
+#include "../../gpu_groth16_prover_3x_b200/csrc/glv_split.cuh"
 
 using namespace mnt753;
 
@@ -391,5 +392,16 @@ int emu_tree_check(uint32_t W, uint32_t k, uint32_t hA_in, const uint64_t *val, 
 void emu_recode(const uint32_t *k, int nl, int c, int W, int32_t *digits) {
     for (int w = 0; w < W; ++w) digits[w] = 0;
     for_each_digit(k, nl, c, W, [&](int w, int d) { digits[w] = d; });
+}
+
+// ---- split of a G2 scalar (csrc/glv_split.cuh): k (24 limbs, plain integer) -> the two stored halves of 12 limbs each,
+// |k_h| with its sign in bit 31 of the top limb -- exactly what k_glv_split leaves for the digit kernels
+void emu_glv_split(int curve, const uint32_t *k_in, uint32_t *out) {
+    uint32_t k[NLIMB], r[2][GLV_L];
+    memcpy(k, k_in, sizeof k);
+    if (curve == 0) glv_split<0>(k, r); else glv_split<1>(k, r);
+    for (int h = 0; h < 2; ++h) memcpy(out + 12 * h, r[h], 48);
+    // limbs 12, 13 of a half must be zero once the sign has been folded into limb 11 (|k_h| < 2^377)
+    out[24] = r[0][12] | r[0][13] | r[1][12] | r[1][13];
 }
 }

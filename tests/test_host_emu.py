@@ -304,3 +304,38 @@ def test_signed_digit_recoding(plan_emu):
                 plan_emu.emu_recode(limbs.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), nl, c, w, digits.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
                 assert digits.min() >= -(1 << (c - 1)) + 1 and digits.max() <= 1 << (c - 1), (c, k)
                 assert sum(int(d) << (c * i) for i, d in enumerate(digits)) == k, (c, k)
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_g2_scalar_split(plan_emu, curve):
+    """csrc/glv_split.cuh -- the arithmetic of k_glv_split, one G2 scalar per thread: k = k0 + k1 (q mod r) modulo r,
+    |k0|, |k1| < 2^377, stored as 12-limb magnitudes with the sign in bit 383 -- for the edges of the decomposition
+    (0, 1, r - 1, lambda and its neighbours, multiples of lambda) and random scalars; lambda from the derivation in
+    tools/gen_constants.py."""
+    import ctypes
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_constants", os.path.join(root, "tools", "gen_constants.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    g = gen.glv_params(curve)
+    lam, r = g["lam"], po.fr_modulus(curve)
+    rng = np.random.default_rng(29 + curve)
+    vals = [0, 1, 2, r - 1, r - 2, lam, lam - 1, lam + 1, (2 * lam) % r, (lam * lam) % r, r // 2, (r - lam) % r, 1 << 752, (1 << 376), (1 << 377) - 1]
+    vals += [int.from_bytes(rng.bytes(100), "little") % r for _ in range(500)]
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    for k in vals:
+        limbs = np.frombuffer(k.to_bytes(96, "little"), dtype=np.uint32).copy()
+        out = np.zeros(25, np.uint32)
+        plan_emu.emu_glv_split(curve, limbs.ctypes.data_as(u32p), out.ctypes.data_as(u32p))
+        assert out[24] == 0, k
+        halves = []
+        for h in range(2):
+            mag = int.from_bytes(out[12 * h:12 * h + 12].tobytes(), "little")
+            sign = mag >> 383
+            mag &= (1 << 383) - 1
+            assert mag.bit_length() <= 377, k
+            halves.append(-mag if sign else mag)
+        assert (halves[0] + halves[1] * lam - k) % r == 0, k
+        assert halves == list(g["split"](k)), k          # and it is the split the constants were derived with
