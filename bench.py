@@ -449,7 +449,11 @@ def run_b200(args):
         "roofline": roofline, "cpu_baseline": cpu_baseline, "clocks": clocks, "strong": strong,
     }
     if world == 1 and not args.no_secondary and not args.quick and (curve, group) == (0, 1):
-        line["secondary"] = secondary_workload(args, local)
+        line["secondary"] = secondary_workload(args, local, 1, 2)                  # MNT6753 G2 (Fq3), BASELINE.json configs[2]
+        try:
+            line["secondary_mnt4753_g2"] = secondary_workload(args, local, 0, 2)  # the B2 query of the headline curve (Fq2)
+        except Exception as e:  # the headline line must not depend on an extra leg
+            line["secondary_mnt4753_g2"] = {"error": str(e)[:300]}
     ctx.close()
     if args.proof != "none" and not args.quick:
         try:
@@ -462,14 +466,14 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
-def secondary_workload(args, device):
+def secondary_workload(args, device, curve, group):
     """BASELINE.json's metric names two workloads; the line's `value` is MNT4753 G1 (configs[1]).  This measures
-    the other one, MNT6753 G2 over the Fq3 twist (configs[2]), the same way (device-resident scalars, CUDA events
-    on the launching stream), with 3 warm-up and 3 timed MSMs, and reports it next to the headline."""
+    another group -- MNT6753 G2 over the Fq3 twist (configs[2]), MNT4753 G2 over Fq2 -- the same way (device-resident
+    scalars, CUDA events on the launching stream), with 3 warm-up and 3 timed MSMs, and reports it next to the headline."""
     import torch
     import gpu_groth16_prover_3x_b200 as pkg
     from gpu_groth16_prover_3x_b200 import synthetic
-    curve, group, n = 1, 2, 1 << args.log_n
+    n = 1 << args.log_n
     ctx = pkg.MsmContext(curve, device)
     try:
         k0, k1 = synthetic.base_seed_scalars(curve)
@@ -493,9 +497,9 @@ def secondary_workload(args, device):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / steps
         t = ctx.last_timings()
-        k_tower = 6
+        k_tower = {1: 1, 2: 3, 3: 6}[pkg.degree(curve, group)]
         macs = float(n) * t["windows"] * 6 * k_tower * 1176
-        return {"workload": "MNT6753 G2 MSM, 2^%d points per GPU" % args.log_n, "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
+        return {"workload": "%s G%d MSM, 2^%d points per GPU" % (CURVE_NAMES[curve], group, args.log_n), "value": n / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms,
                 "steps": steps, "warmup": 3, "window_bits": t["window_bits"], "windows": t["windows"], "window_tables": t["tables"],
                 "table_bytes": binfo["bytes"], "table_build_s": binfo["table_build_ms"] / 1e3, "bases_generation_s": t_bases,
                 "accumulate_gmacs": macs / (t["accumulate"] * 1e-3) / 1e9,
