@@ -14,7 +14,9 @@
 //   the last iFFT scatters through the bit reversal while it multiplies by g^-i / m.
 // One thread per butterfly, one Montgomery product in registers each (fq_mul: 97 % of the IMAD.WIDE pipe).
 #pragma once
+#ifndef MNT753_HOST_EMU
 #include <cuda_runtime.h>
+#endif
 
 #include "fq.cuh"
 

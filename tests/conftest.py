@@ -112,6 +112,22 @@ def plan_emu():
 
 
 @pytest.fixture(scope="session")
+def fft_emu():
+    """The H-polynomial kernels (csrc/fft_kernels.cuh) on a simulated thread block (tests/host_emu/block_sim.hpp)."""
+    import ctypes
+    d = os.path.join(ROOT, "tests", "host_emu")
+    so = os.path.join(d, "libfftemu.so")
+    srcs = [os.path.join(d, "fft_emu.cpp"), os.path.join(d, "block_sim.hpp")] + [os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f)
+                                                                                 for f in ("fft_kernels.cuh", "fq.cuh", "prim.cuh", "mnt753_constants.h")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU", "-x", "c++", srcs[0], "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    lib.emu_compute_h.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p, u64p, u64p, u64p]
+    return lib
+
+
+@pytest.fixture(scope="session")
 def engine_lib():
     import gpu_groth16_prover_3x_b200 as pkg
     return pkg.load_library()

@@ -339,3 +339,27 @@ def test_g2_scalar_split(plan_emu, curve):
             halves.append(-mag if sign else mag)
         assert (halves[0] + halves[1] * lam - k) % r == 0, k
         assert halves == list(g["split"](k)), k          # and it is the split the constants were derived with
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_h_polynomial_kernels_on_a_simulated_block(fft_emu, oracle, golden, curve):
+    """csrc/fft_kernels.cuh -- domain constants, power tables, the NTT kernels (one stage per launch, and the tiled
+    kernel that runs several stages of a tile in shared memory between __syncthreads()), the pointwise steps and the
+    bit-reversing tail -- executed on a simulated thread block (tests/host_emu/block_sim.hpp) in the launch sequence of
+    csrc/fft.cu, against the oracle's restatement of libfqfft's compute_H and against the fixture libfqfft itself
+    produced: sizes 1 .. 1024, tiles cut into one, two and three groups of index bits."""
+    for logm, tiles in ((0, (0,)), (1, (0,)), (3, (0, 2)), (6, (0, 3, 10)), (8, (4, 10)), (10, (10,))):
+        m = 1 << logm
+        ca, cb, cc = (po.gen_scalars(curve, m, 40 + 3 * logm + i) for i in range(3))
+        want = oracle.compute_h(curve, ca, cb, cc)
+        for tile_bits in tiles:
+            out = np.zeros((m + 1) * 12, np.uint64)
+            assert fft_emu.emu_compute_h(curve, logm, tile_bits, _p(ca), _p(cb), _p(cc), _p(out)) == 0
+            assert (out == want).all(), (logm, tile_bits)
+    z = golden["h_vectors"]               # produced by the reference's libfqfft (tools/gen_golden.py)
+    for m in (2, 8, 64, 512):
+        k = "c%d_m%d_" % (curve, m)
+        out = np.zeros((m + 1) * 12, np.uint64)
+        logm = m.bit_length() - 1
+        assert fft_emu.emu_compute_h(curve, logm, 0 if logm < 6 else 5, _p(z[k + "ca"]), _p(z[k + "cb"]), _p(z[k + "cc"]), _p(out)) == 0
+        assert (out == z[k + "out"]).all(), m
