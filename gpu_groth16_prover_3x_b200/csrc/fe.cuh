@@ -26,8 +26,11 @@
 
 namespace mnt753 {
 
+#ifndef MNT753_QUADS_DEFINED
+#define MNT753_QUADS_DEFINED
 constexpr int QUADS = 6;    // uint4 per Fq element
 constexpr int LANES = 32;
+#endif
 
 // Slot operations are real functions on the device (one copy each): the unrolled 24-limb bodies would
 // otherwise be replicated at every call site and push the hot loops out of the instruction cache.

@@ -128,6 +128,23 @@ def fft_emu():
 
 
 @pytest.fixture(scope="session")
+def sort_emu():
+    """The recode / counting-sort kernels (csrc/sort_kernels.cuh) on a simulated thread block."""
+    import ctypes
+    d = os.path.join(ROOT, "tests", "host_emu")
+    so = os.path.join(d, "libsortemu.so")
+    srcs = [os.path.join(d, "sort_emu.cpp"), os.path.join(d, "block_sim.hpp")] + [os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f)
+                                                                                  for f in ("sort_kernels.cuh", "recode.cuh", "fq.cuh", "prim.cuh")]
+    if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU", "-x", "c++", srcs[0], "-o", so], check=True)
+    lib = ctypes.CDLL(so)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    lib.emu_sort.argtypes = [ctypes.c_uint32, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_uint32, ctypes.c_int, ctypes.c_int, u32p,
+                             ctypes.POINTER(ctypes.c_uint8), u32p, u32p, u32p]
+    return lib
+
+
+@pytest.fixture(scope="session")
 def engine_lib():
     import gpu_groth16_prover_3x_b200 as pkg
     return pkg.load_library()

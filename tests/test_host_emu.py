@@ -363,3 +363,68 @@ def test_h_polynomial_kernels_on_a_simulated_block(fft_emu, oracle, golden, curv
         logm = m.bit_length() - 1
         assert fft_emu.emu_compute_h(curve, logm, 0 if logm < 6 else 5, _p(z[k + "ca"]), _p(z[k + "cb"]), _p(z[k + "cc"]), _p(out)) == 0
         assert (out == z[k + "out"]).all(), m
+
+
+def _signed_digits(k, c, w):
+    """The recoding of csrc/recode.cuh restated: digits in [-2^(c-1) + 1, 2^(c-1)], a borrow carried upwards."""
+    out, carry = [], 0
+    for i in range(w):
+        raw = ((k >> (c * i)) & ((1 << c) - 1)) + carry
+        if raw > 1 << (c - 1):
+            out.append(raw - (1 << c)); carry = 1
+        else:
+            out.append(raw); carry = 0
+    return out
+
+
+@pytest.mark.parametrize("c,tables,glv", [(3, 1, 0), (5, 4, 0), (8, 95, 0), (11, 7, 0), (6, 8, 1), (9, 84, 1)])
+def test_counting_sort_on_a_simulated_block(sort_emu, c, tables, glv):
+    """csrc/sort_kernels.cuh -- k_count, the exclusive scan in three kernels, k_scatter -- on a simulated thread block in
+    the launch sequence of enqueue_msm: the histogram counts every non-zero digit of every finite base once, the offsets
+    are its exclusive prefix sums, and the entry list holds, bucket by bucket, exactly the (table row | sign) of those
+    digits -- digit w of a scalar in bucket set w mod G through table w div G; for split G2 scalars the digits of the
+    two signed halves."""
+    import ctypes
+    rng = np.random.default_rng(100 + c)
+    n = 700                                              # three blocks of k_count, the last one ragged
+    bits = 378 if glv else 754
+    wh = (bits + c - 1) // c
+    wd = 2 * wh if glv else wh
+    sets = (wd + tables - 1) // tables
+    if glv:
+        wh = (wh + sets - 1) // sets * sets              # a table belongs to one half (choose_cfg, host_ctx.cuh)
+        wd = 2 * wh
+    nb = 1 << (c - 1)
+    inf = (rng.random(n) < 0.05).astype(np.uint8)
+    scal = np.zeros((n, 24), np.uint32)
+    want = {}
+    for i in range(n):
+        if glv:
+            halves = [int.from_bytes(rng.bytes(48), "little") % (1 << 377) * int(rng.integers(0, 2) * 2 - 1) for _ in range(2)]
+            if i < 4:
+                halves = [(0, 0), ((1 << 377) - 1, -1), (-((1 << 377) - 1), 1), (1 << 376, 0)][i]
+                halves = list(halves)
+            digits = []
+            for h, kh in enumerate(halves):
+                mag = abs(kh) | ((1 << 383) if kh < 0 else 0)
+                scal[i, 12 * h:12 * h + 12] = np.frombuffer(mag.to_bytes(48, "little"), dtype=np.uint32)
+                digits += [(-d if kh < 0 else d) for d in _signed_digits(abs(kh), c, wh)]
+        else:
+            k = int.from_bytes(rng.bytes(96), "little") % (1 << 753) if i >= 3 else (0, (1 << 753) - 1, 1)[i]
+            scal[i] = np.frombuffer(k.to_bytes(96, "little"), dtype=np.uint32)
+            digits = _signed_digits(k, c, wd)
+        if inf[i]:
+            continue
+        for w, d in enumerate(digits):
+            if d:
+                want.setdefault((w % sets) * nb + abs(d) - 1, []).append(((w // sets) * n + i) | (0x80000000 if d < 0 else 0))
+    K = sets * nb
+    total = sum(len(v) for v in want.values())
+    count, offs, entries = np.zeros(K, np.uint32), np.zeros(K + 1, np.uint32), np.zeros(total + 8, np.uint32)
+    u32p = ctypes.POINTER(ctypes.c_uint32)
+    assert sort_emu.emu_sort(n, c, wd, sets, n, glv, wh, scal.ctypes.data_as(u32p), inf.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)),
+                             count.ctypes.data_as(u32p), offs.ctypes.data_as(u32p), entries.ctypes.data_as(u32p)) == 0
+    assert offs[K] == total and offs[0] == 0
+    assert (np.diff(offs.astype(np.int64)) == count).all()
+    for b in range(K):
+        assert sorted(entries[offs[b]:offs[b + 1]].tolist()) == sorted(want.get(b, [])), b
