@@ -114,6 +114,38 @@ MSM_DEVICE bool pair_backward(const Team<F> &T, const BaSlots &s, uint32_t code)
     return pair_backward_tail(T, s, code);
 }
 
+// ---- the UNCLASSIFIED passes of a tile (ba_tile): every pair is taken for a generic addition, x1 != x2.
+// d = (a1 - a2) * b.  Fq: the difference is formed inside the product (Team::mulsub).  Towers: every warp of the
+// team reads all DEG coefficients of the first factor, so the fused form would subtract DEG times over; there the
+// difference goes through the slab once (it replaces a1, which is dead or wanted as the difference in every use).
+template <class F>
+MSM_DEVICE void ba_mul_diff(const Team<F> &T, int d, int a1, int a2, int b, bool pred) {
+    if (F::DEG == 1) T.mulsub(d, a1, a2, b, pred);
+    else { T.sub(a1, a1, a2); T.mul(d, a1, b, pred); }
+}
+template <class F>
+MSM_DEVICE void ba_mul_plain(const Team<F> &T, int d, int a1, int b) {
+    if (F::DEG == 1) T.mulsub(d, a1, -1, b); else T.mul(d, a1, b);
+}
+// forward step: X1, X2 hold the abscissae; the running product INV takes the denominator x2 - x1 (pred: a real addition)
+template <class F>
+MSM_DEVICE void pair_generic_forward(const Team<F> &T, const BaSlots &s, bool pred) {
+    ba_mul_diff(T, s.INV, s.X2, s.X1, s.INV, pred);
+}
+// backward step: X1, Y1, X2, Y2 hold the (signed) operands, PRE the exclusive prefix product, INV the inverse of the
+// inclusive one.  Leaves the sum in (X2, Y2) and the inverse of the shorter prefix in INV (valid: a real addition).
+template <class F>
+MSM_DEVICE void pair_generic_backward(const Team<F> &T, const BaSlots &s, bool valid) {
+    ba_mul_plain(T, s.PRE, s.INV, s.PRE);               // 1 / d
+    ba_mul_diff(T, s.INV, s.X2, s.X1, s.INV, valid);    // inverse of the shorter prefix (towers: X2 <- d)
+    ba_mul_diff(T, s.Y2, s.Y2, s.Y1, s.PRE, true);      // lambda = (y2 - y1) / d
+    if (F::DEG == 3) T.sqr(s.PRE, s.Y2); else ba_mul_plain(T, s.PRE, s.Y2, s.Y2);
+    if (F::DEG == 1) T.sub_sub(s.X2, s.PRE, s.X1, s.X2);                       // x3 = lambda^2 - x1 - x2
+    else { T.sub_sub(s.X2, s.PRE, s.X2, s.X1); T.sub(s.X2, s.X2, s.X1); }     //    = lambda^2 - d - 2 x1
+    ba_mul_diff(T, s.PRE, s.X1, s.X2, s.Y2, true);      // lambda (x1 - x3)
+    T.sub(s.Y2, s.PRE, s.Y1);                           // y3
+}
+
 // After the forward pass INV holds each lane's product of denominators.  Replace it by the lane's own
 // inverse: xor-butterfly product over the 32 lanes, one inversion (lane 0), own = tile^-1 * others.
 // Scratch: S, A, B, C (four distinct slots, all free between the passes).
@@ -196,16 +228,6 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
     // test (two team barriers in the towers), no classification parked in memory and 4 instead of 14 slot operations.
     uint4 nxt, nxt2;
     bool generic = true;
-    // d = (a1 - a2) * b.  Fq: the difference is formed inside the product (Team::mulsub).  Towers: every warp of the
-    // team reads all DEG coefficients of the first factor, so the fused form would subtract DEG times over; there the
-    // difference goes through the slab once (it replaces a1, which is dead or wanted as the difference in every use).
-    auto mul_diff = [&](int d, int a1, int a2, int b, bool pred) {
-        if (DEG == 1) T.mulsub(d, a1, a2, b, pred);
-        else { T.sub(a1, a1, a2); T.mul(d, a1, b, pred); }
-    };
-    auto mul_plain = [&](int d, int a1, int b) {
-        if (DEG == 1) T.mulsub(d, a1, -1, b); else T.mul(d, a1, b);
-    };
     {
         T.set_one(s.INV);
         nxt = src.get(p0 + lane);
@@ -227,7 +249,7 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
             BA_G2S(T, s.X2, g2, has2);
             BA_G2S_WAIT();
             BA_S2G(T, a.scratch + (size_t)d.z * AFFW, s.INV, valid);                // exclusive prefix, parked in the output slot
-            mul_diff(s.INV, s.X2, s.X1, s.INV, valid && has2);
+            pair_generic_forward(T, s, valid && has2);
         }
         if (team_any(T.is_zero(s.INV))) generic = false;
     }
@@ -260,14 +282,7 @@ __device__ __forceinline__ void ba_tile(const Team<F> &T, const BaArgs &a, const
             const bool n1 = valid && (d.x & REF_NEG) != 0u, n2 = valid && (d.y & REF_NEG) != 0u;
             if (team_any(n1)) T.neg_if(s.Y1, s.Y1, n1, valid);
             if (team_any(n2)) T.neg_if(s.Y2, s.Y2, n2, valid);
-            mul_plain(s.PRE, s.INV, s.PRE);               // 1 / d
-            mul_diff(s.INV, s.X2, s.X1, s.INV, valid);    // inverse of the shorter prefix (towers: X2 <- d)
-            mul_diff(s.Y2, s.Y2, s.Y1, s.PRE, true);      // lambda = (y2 - y1) / d
-            if (DEG == 3) T.sqr(s.PRE, s.Y2); else mul_plain(s.PRE, s.Y2, s.Y2);
-            if (DEG == 1) T.sub_sub(s.X2, s.PRE, s.X1, s.X2);                       // x3 = lambda^2 - x1 - x2
-            else { T.sub_sub(s.X2, s.PRE, s.X2, s.X1); T.sub(s.X2, s.X2, s.X1); }  //    = lambda^2 - d - 2 x1
-            mul_diff(s.PRE, s.X1, s.X2, s.Y2, true);      // lambda (x1 - x3)
-            T.sub(s.Y2, s.PRE, s.Y1);                     // y3
+            pair_generic_backward(T, s, valid);
             BA_S2G(T, out, s.X2, valid);
             BA_S2G(T, out + EW, s.Y2, valid);
             if (valid && T.comp == 0) nxt_refs[d.w] = REF_SCRATCH | d.z;

@@ -67,6 +67,7 @@ def emu():
     lib.emu_fq_mul.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, u64p]
     lib.emu_affine_add.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, ctypes.c_int, u64p]
     lib.emu_field_inv.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
+    lib.emu_batch_add_generic.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, ctypes.POINTER(ctypes.c_int), u64p]
     lib.emu_fq_inv.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
     lib.emu_fr_from_mont.argtypes = [ctypes.c_int, ctypes.c_size_t, u64p, u64p]
     return lib

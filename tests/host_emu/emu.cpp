@@ -118,6 +118,40 @@ int affine_add(const uint64_t *p1, const uint64_t *p2, int has2, uint64_t *out) 
     return inf ? 1 : 0;
 }
 
+// The UNCLASSIFIED passes of a tile (ba_tile, batch_affine.cuh) as one lane runs them: B generic additions that share
+// one inversion.  flags[i] bit 0 / 1: operand 1 / 2 is referenced with the negation flag (its ordinate is negated after
+// the load, as the kernel does).  Returns 1 when the product of the denominators is zero (the kernel then runs the
+// classified passes instead) and leaves out untouched.
+template <class G>
+int batch_add_generic(size_t B, const uint64_t *p1, const uint64_t *p2, const int *flags, uint64_t *out) {
+    Emu<G> E;
+    const size_t st = 12 * Emu<G>::DEG;
+    const BaSlots s = {0, 1, 2, 3, 4, 5};
+    const int PARK = 6;
+    std::vector<uint64_t> prefix(B * st);
+    E.T.set_one(s.INV);
+    for (size_t i = 0; i < B; ++i) {
+        E.put(s.X1, p1 + 2 * i * st);
+        E.put(s.X2, p2 + 2 * i * st);
+        E.T.copy(PARK, s.INV);
+        E.get(PARK, prefix.data() + i * st);                  // exclusive prefix, parked in the addition's output slot
+        pair_generic_forward(E.T, s, true);
+    }
+    if (E.T.is_zero(s.INV)) return 1;
+    tile_inverse(E.T, s.INV, s.X1, s.Y1, s.X2, s.Y2);
+    for (size_t k = B; k-- > 0;) {
+        E.put(s.X1, p1 + 2 * k * st); E.put(s.Y1, p1 + 2 * k * st + st);
+        E.put(s.X2, p2 + 2 * k * st); E.put(s.Y2, p2 + 2 * k * st + st);
+        E.put(s.PRE, prefix.data() + k * st);
+        if (flags[k] & 1) E.T.neg_if(s.Y1, s.Y1, true, true);
+        if (flags[k] & 2) E.T.neg_if(s.Y2, s.Y2, true, true);
+        pair_generic_backward(E.T, s, true);
+        E.get(s.X2, out + 2 * k * st);
+        E.get(s.Y2, out + 2 * k * st + st);
+    }
+    return 0;
+}
+
 template <class G>
 int field_inv(size_t n, const uint64_t *a, uint64_t *out) {
     Emu<G> E;
@@ -138,6 +172,13 @@ int emu_affine_add(int curve, int group, const uint64_t *p1, const uint64_t *p2,
     if (curve == 0 && group == 2) return affine_add<Mnt4G2>(p1, p2, has2, out);
     if (curve == 1 && group == 1) return affine_add<Mnt6G1>(p1, p2, has2, out);
     if (curve == 1 && group == 2) return affine_add<Mnt6G2>(p1, p2, has2, out);
+    return -1;
+}
+int emu_batch_add_generic(int curve, int group, size_t B, const uint64_t *p1, const uint64_t *p2, const int *flags, uint64_t *out) {
+    if (curve == 0 && group == 1) return batch_add_generic<Mnt4G1>(B, p1, p2, flags, out);
+    if (curve == 0 && group == 2) return batch_add_generic<Mnt4G2>(B, p1, p2, flags, out);
+    if (curve == 1 && group == 1) return batch_add_generic<Mnt6G1>(B, p1, p2, flags, out);
+    if (curve == 1 && group == 2) return batch_add_generic<Mnt6G2>(B, p1, p2, flags, out);
     return -1;
 }
 int emu_field_inv(int curve, int group, size_t n, const uint64_t *a, uint64_t *out) {

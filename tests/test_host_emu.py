@@ -428,3 +428,31 @@ def test_counting_sort_on_a_simulated_block(sort_emu, c, tables, glv):
     assert (np.diff(offs.astype(np.int64)) == count).all()
     for b in range(K):
         assert sorted(entries[offs[b]:offs[b + 1]].tolist()) == sorted(want.get(b, [])), b
+
+
+@pytest.mark.parametrize("curve,group", CG)
+def test_emu_generic_tile(emu, oracle, curve, group):
+    """The UNCLASSIFIED passes of a tile -- the hot path of the accumulation (batch_affine.cuh: pair_generic_forward,
+    one inversion for the whole batch, pair_generic_backward; for Fq the differences are formed inside the product,
+    Team::mulsub) -- on batches of 1, 2 and 9 generic additions with every combination of negated operands, against
+    the oracle's point addition; and a batch that holds a doubling reports a zero product (the kernel's cue to run the
+    classified passes)."""
+    import ctypes
+    deg = po.degree(curve, group)
+    w = 24 * deg
+    pts = oracle.gen_bases(curve, group, 24).reshape(-1, w)
+    for batch in (1, 2, 9):
+        p1 = np.ascontiguousarray(pts[:batch])
+        p2 = np.ascontiguousarray(pts[12:12 + batch])
+        flags = np.array([(i * 7 + batch) % 4 for i in range(batch)], np.int32)
+        out = np.zeros_like(p1)
+        assert emu.emu_batch_add_generic(curve, group, batch, _p(p1), _p(p2), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(out)) == 0
+        for i in range(batch):
+            a = oracle.point_op(curve, group, 4, p1[i]) if flags[i] & 1 else p1[i]
+            b = oracle.point_op(curve, group, 4, p2[i]) if flags[i] & 2 else p2[i]
+            assert (out[i] == oracle.point_op(curve, group, 0, a, b)).all(), (batch, i)
+    p1 = np.ascontiguousarray(pts[:3])
+    p2 = np.ascontiguousarray(pts[[5, 1, 7]])                # the middle pair is P + P
+    out = np.zeros_like(p1)
+    flags = np.zeros(3, np.int32)
+    assert emu.emu_batch_add_generic(curve, group, 3, _p(p1), _p(p2), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(out)) == 1
