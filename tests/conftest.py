@@ -55,7 +55,7 @@ def emu():
     extra = os.environ.get("EMU_CFLAGS", "").split()   # e.g. -DMNT753_MUL_ROLL=8 to emulate a multiplier variant
     so = os.path.join(d, "libemu%s.so" % ("_" + "".join(c for c in "".join(extra) if c.isalnum()) if extra else ""))
     srcs = [os.path.join(d, "emu.cpp")] + [os.path.join(ROOT, "gpu_groth16_prover_3x_b200", "csrc", f)
-                                            for f in ("prim.cuh", "fq.cuh", "fe.cuh", "ec.cuh", "curves.cuh", "batch_affine.cuh")]
+                                            for f in ("prim.cuh", "fq.cuh", "fe.cuh", "ec.cuh", "curves.cuh", "batch_affine.cuh", "glv_split.cuh")]
     srcs += [os.path.join(ROOT, "tools", "experiments", f) for f in ("fq_fp64.cuh", "fq_experiments.cuh")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.run(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-DMNT753_HOST_EMU"] + extra + ["-x", "c++",
@@ -67,6 +67,7 @@ def emu():
     lib.emu_fq_mul.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, u64p]
     lib.emu_affine_add.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, ctypes.c_int, u64p]
     lib.emu_field_inv.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
+    lib.emu_psi.argtypes = [ctypes.c_int, u64p, u64p]
     lib.emu_batch_add_generic.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p, ctypes.POINTER(ctypes.c_int), u64p]
     lib.emu_fq_inv.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
     lib.emu_fr_from_mont.argtypes = [ctypes.c_int, ctypes.c_size_t, u64p, u64p]

@@ -9,6 +9,7 @@
 
 #include "../../gpu_groth16_prover_3x_b200/csrc/curves.cuh"
 #include "../../gpu_groth16_prover_3x_b200/csrc/batch_affine.cuh"
+#include "../../gpu_groth16_prover_3x_b200/csrc/glv_split.cuh"
 #include "../../tools/experiments/fq_fp64.cuh"
 #include "../../tools/experiments/fq_experiments.cuh"
 
@@ -152,6 +153,23 @@ int batch_add_generic(size_t B, const uint64_t *p1, const uint64_t *p2, const in
     return 0;
 }
 
+// psi(x, y) = (cX Frob(x), cY Frob(y)) of an affine G2 point, the steps of k_psi_many (glv.cuh)
+template <class G>
+int psi_point(const uint64_t *p, uint64_t *out) {
+    typedef Glv<G::CURVE> K;
+    Emu<G> E;
+    const size_t st = 12 * Emu<G>::DEG;
+    E.put(0, p); E.put(1, p + st);
+    E.T.frob(2, 0, 1);
+    E.T.frob(3, 1, 1);
+    fq_t cx, cy;
+    for (int i = 0; i < NLIMB; ++i) { cx[i] = K::TWX(i); cy[i] = K::TWY(i); }
+    E.T.scale_fq(2, 2, cx);
+    E.T.scale_fq(3, 3, cy);
+    E.get(2, out); E.get(3, out + st);
+    return 0;
+}
+
 template <class G>
 int field_inv(size_t n, const uint64_t *a, uint64_t *out) {
     Emu<G> E;
@@ -180,6 +198,9 @@ int emu_batch_add_generic(int curve, int group, size_t B, const uint64_t *p1, co
     if (curve == 1 && group == 1) return batch_add_generic<Mnt6G1>(B, p1, p2, flags, out);
     if (curve == 1 && group == 2) return batch_add_generic<Mnt6G2>(B, p1, p2, flags, out);
     return -1;
+}
+int emu_psi(int curve, const uint64_t *p, uint64_t *out) {
+    return curve == 0 ? psi_point<Mnt4G2>(p, out) : psi_point<Mnt6G2>(p, out);
 }
 int emu_field_inv(int curve, int group, size_t n, const uint64_t *a, uint64_t *out) {
     if (curve == 0 && group == 1) return field_inv<Mnt4G1>(n, a, out);

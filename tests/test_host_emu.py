@@ -456,3 +456,25 @@ def test_emu_generic_tile(emu, oracle, curve, group):
     out = np.zeros_like(p1)
     flags = np.zeros(3, np.int32)
     assert emu.emu_batch_add_generic(curve, group, 3, _p(p1), _p(p2), flags.ctypes.data_as(ctypes.POINTER(ctypes.c_int)), _p(out)) == 1
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_emu_twist_frobenius(emu, oracle, curve):
+    """psi(x, y) = (cX Frob(x), cY Frob(y)) -- the map k_psi_many derives the upper half of the G2 window tables with
+    (csrc/glv.cuh; libff G2::mul_by_q, mnt4753_g2.cpp:364-368) -- is multiplication by lambda = q mod r: the steps of the
+    kernel on the host against the oracle's scalar multiplication, and psi of infinity (all zero) stays infinity."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("gen_constants", os.path.join(root, "tools", "gen_constants.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    lam, r = gen.glv_params(curve)["lam"], po.fr_modulus(curve)
+    k = po.int_to_limbs(lam * po.R % r)
+    w = 24 * po.degree(curve, 2)
+    for p in oracle.gen_bases(curve, 2, 6).reshape(-1, w):
+        out = np.zeros(w, np.uint64)
+        assert emu.emu_psi(curve, _p(p), _p(out)) == 0
+        assert (out == oracle.point_op(curve, 2, 3, p, k=k)).all()
+    out = np.ones(w, np.uint64)
+    assert emu.emu_psi(curve, _p(np.zeros(w, np.uint64)), _p(out)) == 0 and not out.any()
