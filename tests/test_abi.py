@@ -133,3 +133,21 @@ def test_parallel_file_reader(engine_lib, tmp_path):
     assert f(str(path).encode(), n - 100, 200, out.ctypes.data) == 1                 # short file, single slice
     assert f(str(path).encode(), n - (20 << 20), 32 << 20, out.ctypes.data) == 1     # short file, several slices
     assert f(b"/nonexistent/blob", 0, 1, out.ctypes.data) == -1
+
+
+def test_argument_checks_need_no_gpu(engine_lib):
+    """Entry points reject null contexts / keys before they touch CUDA (error behaviour of the boundary: a status code,
+    never a crash, never a point)."""
+    vp = ctypes.c_void_p
+    keys = (vp * 2)()
+    assert engine_lib.b200msm_key_load_sharded_file(None, 2, b"/nonexistent", keys) == 1
+    ctxs = (vp * 2)()                                            # two null contexts
+    assert engine_lib.b200msm_key_load_sharded_file(ctxs, 2, b"/nonexistent", keys) == 1
+    assert engine_lib.b200msm_set_lane_sms(None, 0, 8) == 1
+    assert engine_lib.b200msm_msm(None, 0, 0, None, 0, None) == 1
+    assert engine_lib.b200msm_wait(None, 0) == 1
+    assert engine_lib.b200msm_prove(None, None, None, 0, None) == 1
+    assert engine_lib.b200msm_proof_bytes(None) == 0 and engine_lib.b200msm_input_bytes(None) == 0
+    assert engine_lib.b200msm_last_error(None) == b"null context"
+    off, ln = ctypes.c_size_t(), ctypes.c_size_t()
+    assert engine_lib.b200msm_shard_range(10, 0, 1, None, ctypes.byref(ln)) == 1
