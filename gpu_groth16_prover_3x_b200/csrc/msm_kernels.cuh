@@ -3,13 +3,13 @@
 //
 //   k_flag_inf        once per base set: mark bases encoded as infinity (y == 0)
 //   k_from_mont       scalars: Montgomery -> integer (reference: reduce.cu:35-36)
-//   k_count           signed-digit recode, histogram of (window, bucket) keys
-//   k_scan_*          exclusive prefix sum of the histogram
-//   k_scatter         single-pass radix (counting) sort: point indices grouped by (window, bucket)
-//   k_batch_add       bucket accumulation (batch_affine.cuh): rounds of pairwise affine additions, one
-//   k_ba_fixup        persistent launch, every team takes its share of the sorted list through all rounds
-//   k_tree_round      bucket reduction  sum_b (b + 1) B_b  as a tree of pairwise affine additions (bucket_tree.cuh):
-//   k_tree_finish     one launch per level, then the k + 1 short lists of every set
+//   k_count           signed-digit recode (recode.cuh), histogram of (window, bucket) keys      } sort_kernels.cuh
+//   k_scan_*          exclusive prefix sum of the histogram                                      }
+//   k_scatter         single-pass radix (counting) sort: point indices grouped by (window, bucket) }
+//   k_batch_add       bucket accumulation (batch_affine.cuh, round planning in ba_plan.cuh): rounds of pairwise affine
+//   k_ba_fixup        additions, one persistent launch, every team takes its share of the sorted list through all rounds
+//   k_tree_round      bucket reduction  sum_b (b + 1) B_b  as a tree of pairwise affine additions (bucket_tree.cuh, index
+//   k_tree_finish     logic in tree_plan.cuh): one launch per level, then the k + 1 short lists of every set
 //   k_sum             plain segmented sums (the terms of a set -> its window sum; partial results of shards)
 //   k_horner          window combine: result = sum_w 2^(c*w) * S_w
 //
